@@ -1,0 +1,380 @@
+// ctb200.cu -- C ABI of libctb200.so (declared in include/ctb200.h).  sm_100a only.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ctb200.h"
+#include "ctb_positions.cuh"
+#include "ctb_generic.cuh"
+#include "ctb_sorted.cuh"
+
+namespace {
+
+thread_local int g_last_cuda_error = 0;
+
+inline int cuda_fail(cudaError_t e) {
+  g_last_cuda_error = (int)e;
+  return CTB_ERR_CUDA;
+}
+
+inline int cuda_status(cudaError_t e) {
+  if (e == cudaSuccess) return CTB_OK;
+  if (e == cudaErrorNotSupported) return CTB_ERR_UNSUPPORTED;
+  return cuda_fail(e);
+}
+
+#define CTB_CUDA(expr)                                \
+  do {                                                \
+    cudaError_t _e = (expr);                          \
+    if (_e != cudaSuccess) return cuda_fail(_e);      \
+  } while (0)
+
+#define CTB_LAUNCH_CHECK()                            \
+  do {                                                \
+    cudaError_t _e = cudaGetLastError();              \
+    if (_e != cudaSuccess) return cuda_fail(_e);      \
+  } while (0)
+
+int check_shape(const ctb_shape* s, bool need_f) {
+  if (!s) return CTB_ERR_INVALID_ARGUMENT;
+  if (s->B <= 0 || s->H <= 0 || s->N <= 0) return CTB_ERR_INVALID_ARGUMENT;
+  if (need_f && s->F <= 0) return CTB_ERR_INVALID_ARGUMENT;
+  if (s->dim != 2 && s->dim != 3) return CTB_ERR_INVALID_ARGUMENT;
+  long long C = 1;
+  for (int a = 0; a < s->dim; ++a) {
+    if (s->size[a] < 2) return CTB_ERR_INVALID_ARGUMENT;
+    C *= s->size[a];
+    if (C >= (1ll << 30)) return CTB_ERR_UNSUPPORTED;
+  }
+  const long long S = 1ll << s->dim;
+  if (S * (long long)s->N >= (1ll << 31) - 1) return CTB_ERR_UNSUPPORTED;  // arg is int32
+  const long long units = (long long)s->B * s->H;
+  const long long chunks = (s->N + ctb::kGenericBlock - 1) / ctb::kGenericBlock;
+  if (units * chunks >= (1ll << 31) - 1) return CTB_ERR_UNSUPPORTED;
+  return CTB_OK;
+}
+
+inline long long cells(const ctb_shape* s) {
+  long long C = 1;
+  for (int a = 0; a < s->dim; ++a) C *= s->size[a];
+  return C;
+}
+
+struct Launch {
+  int chunks;
+  unsigned blocks;
+  cudaStream_t stream;
+};
+
+inline Launch make_launch(const ctb_shape* s, void* stream) {
+  Launch l;
+  l.chunks = (s->N + ctb::kGenericBlock - 1) / ctb::kGenericBlock;
+  l.blocks = (unsigned)((long long)s->B * s->H * l.chunks);
+  l.stream = (cudaStream_t)stream;
+  return l;
+}
+
+// ---- typed implementations ----------------------------------------------------------------------
+template <int D>
+int positions_fwd_impl(const float* keys, float* lc, int64_t* idx, const ctb_shape* s, void* stream) {
+  const ctb::Grid<D> g = ctb::make_grid<D>(s->size);
+  const Launch l = make_launch(s, stream);
+  ctb::positions_fwd_kernel<D><<<l.blocks, ctb::kGenericBlock, 0, l.stream>>>(keys, lc, (long long*)idx, g,
+                                                                              s->N, l.chunks);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+template <int D>
+int positions_bwd_impl(const float* keys, const float* grad_lc, float* grad_keys, const ctb_shape* s,
+                       void* stream) {
+  const ctb::Grid<D> g = ctb::make_grid<D>(s->size);
+  const Launch l = make_launch(s, stream);
+  ctb::positions_bwd_kernel<D><<<l.blocks, ctb::kGenericBlock, 0, l.stream>>>(keys, grad_lc, grad_keys, g,
+                                                                              s->N, l.chunks);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+template <int D, bool KEYS>
+int splat_fwd_atomic_impl(ctb::PointSource src, const float* feat, const float* pad, float* z, int32_t* arg,
+                          const ctb_shape* s, int reduce, void* stream) {
+  const ctb::Grid<D> g = ctb::make_grid<D>(s->size);
+  const Launch l = make_launch(s, stream);
+  const size_t n_grid = (size_t)s->B * s->H * s->F * g.C;
+  CTB_CUDA(cudaMemsetAsync(z, 0, n_grid * sizeof(float), l.stream));
+  if (reduce == CTB_REDUCE_SUM) {
+    ctb::splat_fwd_atomic_kernel<D, KEYS, 0, true><<<l.blocks, ctb::kGenericBlock, 0, l.stream>>>(
+        src, feat, pad, z, nullptr, g, s->H, s->F, s->N, l.chunks);
+    CTB_LAUNCH_CHECK();
+    return CTB_OK;
+  }
+  CTB_CUDA(cudaMemsetAsync(arg, 0xFF, n_grid * sizeof(int32_t), l.stream));
+  ctb::splat_fwd_atomic_kernel<D, KEYS, 0, false><<<l.blocks, ctb::kGenericBlock, 0, l.stream>>>(
+      src, feat, pad, z, arg, g, s->H, s->F, s->N, l.chunks);
+  CTB_LAUNCH_CHECK();
+  ctb::splat_fwd_atomic_kernel<D, KEYS, 1, false><<<l.blocks, ctb::kGenericBlock, 0, l.stream>>>(
+      src, feat, pad, z, arg, g, s->H, s->F, s->N, l.chunks);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+template <int D, bool KEYS>
+int splat_bwd_impl(ctb::PointSource src, const float* feat, const float* pad, const float* grad_z,
+                   const int32_t* arg, float* grad_feat, float* grad_pos, const ctb_shape* s, int reduce,
+                   void* stream) {
+  const ctb::Grid<D> g = ctb::make_grid<D>(s->size);
+  const Launch l = make_launch(s, stream);
+  if (reduce == CTB_REDUCE_SUM)
+    ctb::splat_bwd_kernel<D, KEYS, true><<<l.blocks, ctb::kGenericBlock, 0, l.stream>>>(
+        src, feat, pad, grad_z, arg, grad_feat, grad_pos, g, s->H, s->F, s->N, l.chunks);
+  else
+    ctb::splat_bwd_kernel<D, KEYS, false><<<l.blocks, ctb::kGenericBlock, 0, l.stream>>>(
+        src, feat, pad, grad_z, arg, grad_feat, grad_pos, g, s->H, s->F, s->N, l.chunks);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+template <int D, bool KEYS>
+int slice_fwd_impl(ctb::PointSource src, const float* grid, const float* pad, float* out, const ctb_shape* s,
+                   void* stream) {
+  const ctb::Grid<D> g = ctb::make_grid<D>(s->size);
+  const Launch l = make_launch(s, stream);
+  ctb::slice_fwd_kernel<D, KEYS><<<l.blocks, ctb::kGenericBlock, 0, l.stream>>>(src, grid, pad, out, g, s->H,
+                                                                                s->F, s->N, l.chunks);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+template <int D, bool KEYS>
+int slice_bwd_atomic_impl(ctb::PointSource src, const float* grid, const float* pad, const float* grad_out,
+                          float* grad_grid, float* grad_pos, const ctb_shape* s, void* stream) {
+  const ctb::Grid<D> g = ctb::make_grid<D>(s->size);
+  const Launch l = make_launch(s, stream);
+  CTB_CUDA(cudaMemsetAsync(grad_grid, 0, (size_t)s->B * s->H * s->F * g.C * sizeof(float), l.stream));
+  ctb::slice_bwd_kernel<D, KEYS, true><<<l.blocks, ctb::kGenericBlock, 0, l.stream>>>(
+      src, grid, pad, grad_out, grad_grid, grad_pos, g, s->H, s->F, s->N, l.chunks);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+#define CTB_DISPATCH_DIM(shape, call2, call3) ((shape)->dim == 2 ? (call2) : (call3))
+
+}  // namespace
+
+// ---- exported entries -----------------------------------------------------------------------------
+extern "C" {
+
+int ctb_version(void) { return CTB_VERSION; }
+
+const char* ctb_strerror(int status) {
+  switch (status) {
+    case CTB_OK: return "ok";
+    case CTB_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case CTB_ERR_UNSUPPORTED: return "unsupported shape";
+    case CTB_ERR_CUDA: return "CUDA runtime error (see ctb_last_cuda_error)";
+    case CTB_ERR_WORKSPACE: return "plan / workspace missing or too small";
+    default: return "unknown status";
+  }
+}
+
+int ctb_last_cuda_error(void) { return g_last_cuda_error; }
+
+int ctb_positions_fwd(const float* keys, float* lc, int64_t* idx, const ctb_shape* shape, void* stream) {
+  int st = check_shape(shape, false);
+  if (st) return st;
+  if (!keys || !lc || !idx) return CTB_ERR_INVALID_ARGUMENT;
+  return CTB_DISPATCH_DIM(shape, positions_fwd_impl<2>(keys, lc, idx, shape, stream),
+                          positions_fwd_impl<3>(keys, lc, idx, shape, stream));
+}
+
+int ctb_positions_bwd(const float* keys, const float* grad_lc, float* grad_keys, const ctb_shape* shape,
+                      void* stream) {
+  int st = check_shape(shape, false);
+  if (st) return st;
+  if (!keys || !grad_lc || !grad_keys) return CTB_ERR_INVALID_ARGUMENT;
+  return CTB_DISPATCH_DIM(shape, positions_bwd_impl<2>(keys, grad_lc, grad_keys, shape, stream),
+                          positions_bwd_impl<3>(keys, grad_lc, grad_keys, shape, stream));
+}
+
+int ctb_splat_fwd(const float* lc, const int64_t* idx, const float* features, const float* pad, float* z,
+                  int32_t* arg, const ctb_shape* shape, int reduce, void* stream) {
+  int st = check_shape(shape, true);
+  if (st) return st;
+  if (!lc || !idx || !features || !z) return CTB_ERR_INVALID_ARGUMENT;
+  if (reduce != CTB_REDUCE_MAX && reduce != CTB_REDUCE_SUM) return CTB_ERR_INVALID_ARGUMENT;
+  if (reduce == CTB_REDUCE_MAX && !arg) return CTB_ERR_INVALID_ARGUMENT;
+  ctb::PointSource src{nullptr, lc, idx};
+  return CTB_DISPATCH_DIM(shape,
+                          (splat_fwd_atomic_impl<2, false>(src, features, pad, z, arg, shape, reduce, stream)),
+                          (splat_fwd_atomic_impl<3, false>(src, features, pad, z, arg, shape, reduce, stream)));
+}
+
+int ctb_splat_bwd(const float* lc, const int64_t* idx, const float* features, const float* pad,
+                  const float* grad_z, const int32_t* arg, float* grad_features, float* grad_lc,
+                  const ctb_shape* shape, int reduce, void* stream) {
+  int st = check_shape(shape, true);
+  if (st) return st;
+  if (!lc || !idx || !features || !grad_z || !grad_features || !grad_lc) return CTB_ERR_INVALID_ARGUMENT;
+  if (reduce != CTB_REDUCE_MAX && reduce != CTB_REDUCE_SUM) return CTB_ERR_INVALID_ARGUMENT;
+  if (reduce == CTB_REDUCE_MAX && !arg) return CTB_ERR_INVALID_ARGUMENT;
+  ctb::PointSource src{nullptr, lc, idx};
+  return CTB_DISPATCH_DIM(
+      shape,
+      (splat_bwd_impl<2, false>(src, features, pad, grad_z, arg, grad_features, grad_lc, shape, reduce, stream)),
+      (splat_bwd_impl<3, false>(src, features, pad, grad_z, arg, grad_features, grad_lc, shape, reduce, stream)));
+}
+
+int ctb_slice_fwd(const float* lc, const int64_t* idx, const float* grid, const float* pad, float* out,
+                  const ctb_shape* shape, void* stream) {
+  int st = check_shape(shape, true);
+  if (st) return st;
+  if (!lc || !idx || !grid || !out) return CTB_ERR_INVALID_ARGUMENT;
+  ctb::PointSource src{nullptr, lc, idx};
+  return CTB_DISPATCH_DIM(shape, (slice_fwd_impl<2, false>(src, grid, pad, out, shape, stream)),
+                          (slice_fwd_impl<3, false>(src, grid, pad, out, shape, stream)));
+}
+
+int ctb_slice_bwd(const float* lc, const int64_t* idx, const float* grid, const float* pad,
+                  const float* grad_out, float* grad_grid, float* grad_lc, const ctb_shape* shape,
+                  void* stream) {
+  int st = check_shape(shape, true);
+  if (st) return st;
+  if (!lc || !idx || !grid || !grad_out || !grad_grid || !grad_lc) return CTB_ERR_INVALID_ARGUMENT;
+  ctb::PointSource src{nullptr, lc, idx};
+  return CTB_DISPATCH_DIM(
+      shape, (slice_bwd_atomic_impl<2, false>(src, grid, pad, grad_out, grad_grid, grad_lc, shape, stream)),
+      (slice_bwd_atomic_impl<3, false>(src, grid, pad, grad_out, grad_grid, grad_lc, shape, stream)));
+}
+
+int ctb_deterministic_supported(const ctb_shape* shape, int op, int reduce) {
+  if (check_shape(shape, true)) return 0;
+  const bool sum = reduce == CTB_REDUCE_SUM;
+  ctb::ScatterConfig sc;
+  ctb::GatherConfig gc;
+  switch (op) {
+    case CTB_OP_SPLAT_FWD: return ctb::plan_supported(shape) && ctb::scatter_config(shape, sum, &sc);
+    case CTB_OP_SPLAT_BWD: return sum ? 0 : ctb::gather_config(shape, ctb::GATHER_SPLAT_BWD, &gc);
+    case CTB_OP_SLICE_FWD: return ctb::gather_config(shape, ctb::GATHER_SLICE_FWD, &gc);
+    case CTB_OP_SLICE_BWD:
+      return ctb::plan_supported(shape) && ctb::scatter_config(shape, true, &sc) &&
+             ctb::gather_config(shape, ctb::GATHER_SLICE_BWD_KEYS, &gc);
+    default: return 0;
+  }
+}
+
+size_t ctb_plan_bytes(const ctb_shape* shape) {
+  if (check_shape(shape, false)) return 0;
+  if (!ctb::plan_supported(shape)) return 0;
+  return ctb::sorted_plan_bytes(shape);
+}
+
+int ctb_plan_build(const float* keys, void* plan, size_t plan_bytes, const ctb_shape* shape, void* stream) {
+  int st = check_shape(shape, false);
+  if (st) return st;
+  if (!keys || !plan) return CTB_ERR_INVALID_ARGUMENT;
+  if (!ctb::plan_supported(shape)) return CTB_ERR_UNSUPPORTED;
+  if (plan_bytes < ctb::sorted_plan_bytes(shape)) return CTB_ERR_WORKSPACE;
+  return cuda_status(shape->dim == 2 ? ctb::sorted_plan_build<2>(keys, plan, shape, (cudaStream_t)stream)
+                                     : ctb::sorted_plan_build<3>(keys, plan, shape, (cudaStream_t)stream));
+}
+
+int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pad, float* z, int32_t* arg,
+                       const ctb_shape* shape, int reduce, int mode, const void* plan, void* stream) {
+  int st = check_shape(shape, true);
+  if (st) return st;
+  if (!keys || !features || !z) return CTB_ERR_INVALID_ARGUMENT;
+  if (reduce != CTB_REDUCE_MAX && reduce != CTB_REDUCE_SUM) return CTB_ERR_INVALID_ARGUMENT;
+  if (reduce == CTB_REDUCE_MAX && !arg) return CTB_ERR_INVALID_ARGUMENT;
+  if (mode == CTB_MODE_DETERMINISTIC) {
+    if (!plan) return CTB_ERR_WORKSPACE;
+    const bool sum = reduce == CTB_REDUCE_SUM;
+    return cuda_status(shape->dim == 2
+                           ? ctb::sorted_scatter<2>(plan, features, pad, z, arg, shape, sum, (cudaStream_t)stream)
+                           : ctb::sorted_scatter<3>(plan, features, pad, z, arg, shape, sum, (cudaStream_t)stream));
+  }
+  if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;
+  ctb::PointSource src{keys, nullptr, nullptr};
+  return CTB_DISPATCH_DIM(shape,
+                          (splat_fwd_atomic_impl<2, true>(src, features, pad, z, arg, shape, reduce, stream)),
+                          (splat_fwd_atomic_impl<3, true>(src, features, pad, z, arg, shape, reduce, stream)));
+}
+
+int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pad, const float* grad_z,
+                       const int32_t* arg, float* grad_features, float* grad_keys, const ctb_shape* shape,
+                       int reduce, int mode, void* stream) {
+  int st = check_shape(shape, true);
+  if (st) return st;
+  if (!keys || !features || !grad_z || !grad_features || !grad_keys) return CTB_ERR_INVALID_ARGUMENT;
+  if (reduce != CTB_REDUCE_MAX && reduce != CTB_REDUCE_SUM) return CTB_ERR_INVALID_ARGUMENT;
+  if (reduce == CTB_REDUCE_MAX && !arg) return CTB_ERR_INVALID_ARGUMENT;
+  if (mode == CTB_MODE_DETERMINISTIC) {
+    if (reduce != CTB_REDUCE_MAX) return CTB_ERR_UNSUPPORTED;
+    return cuda_status(shape->dim == 2
+                           ? (ctb::tile_gather<2, ctb::GATHER_SPLAT_BWD>(keys, grad_z, arg, features, pad, grad_features,
+                                                                        grad_keys, shape, (cudaStream_t)stream))
+                           : (ctb::tile_gather<3, ctb::GATHER_SPLAT_BWD>(keys, grad_z, arg, features, pad, grad_features,
+                                                                        grad_keys, shape, (cudaStream_t)stream)));
+  }
+  if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;
+  ctb::PointSource src{keys, nullptr, nullptr};
+  return CTB_DISPATCH_DIM(
+      shape,
+      (splat_bwd_impl<2, true>(src, features, pad, grad_z, arg, grad_features, grad_keys, shape, reduce, stream)),
+      (splat_bwd_impl<3, true>(src, features, pad, grad_z, arg, grad_features, grad_keys, shape, reduce, stream)));
+}
+
+int ctb_slice_fwd_keys(const float* keys, const float* grid, const float* pad, float* out,
+                       const ctb_shape* shape, int mode, void* stream) {
+  int st = check_shape(shape, true);
+  if (st) return st;
+  if (!keys || !grid || !out) return CTB_ERR_INVALID_ARGUMENT;
+  if (mode == CTB_MODE_DETERMINISTIC)
+    return cuda_status(shape->dim == 2
+                           ? (ctb::tile_gather<2, ctb::GATHER_SLICE_FWD>(keys, grid, nullptr, nullptr, pad, out, nullptr,
+                                                                        shape, (cudaStream_t)stream))
+                           : (ctb::tile_gather<3, ctb::GATHER_SLICE_FWD>(keys, grid, nullptr, nullptr, pad, out, nullptr,
+                                                                        shape, (cudaStream_t)stream)));
+  if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;
+  ctb::PointSource src{keys, nullptr, nullptr};
+  return CTB_DISPATCH_DIM(shape, (slice_fwd_impl<2, true>(src, grid, pad, out, shape, stream)),
+                          (slice_fwd_impl<3, true>(src, grid, pad, out, shape, stream)));
+}
+
+int ctb_slice_bwd_keys(const float* keys, const float* grid, const float* pad, const float* grad_out,
+                       float* grad_grid, float* grad_keys, const ctb_shape* shape, int mode, const void* plan,
+                       void* stream) {
+  int st = check_shape(shape, true);
+  if (st) return st;
+  if (!keys || !grid || !grad_out || !grad_grid || !grad_keys) return CTB_ERR_INVALID_ARGUMENT;
+  if (mode == CTB_MODE_DETERMINISTIC) {
+    if (!plan) return CTB_ERR_WORKSPACE;
+    if (!ctb_deterministic_supported(shape, CTB_OP_SLICE_BWD, CTB_REDUCE_SUM)) return CTB_ERR_UNSUPPORTED;
+    // grad_grid: cell-stationary scatter-add of grad_out * pad (the Splat-sum kernel) ...
+    st = cuda_status(shape->dim == 2
+                         ? ctb::sorted_scatter<2>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream)
+                         : ctb::sorted_scatter<3>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream));
+    if (st) return st;
+    // ... and grad_keys: tile gather against the convolved grid.
+    return cuda_status(shape->dim == 2
+                           ? (ctb::tile_gather<2, ctb::GATHER_SLICE_BWD_KEYS>(keys, grid, nullptr, grad_out, pad, nullptr,
+                                                                             grad_keys, shape, (cudaStream_t)stream))
+                           : (ctb::tile_gather<3, ctb::GATHER_SLICE_BWD_KEYS>(keys, grid, nullptr, grad_out, pad, nullptr,
+                                                                             grad_keys, shape, (cudaStream_t)stream)));
+  }
+  if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;
+  ctb::PointSource src{keys, nullptr, nullptr};
+  return CTB_DISPATCH_DIM(
+      shape, (slice_bwd_atomic_impl<2, true>(src, grid, pad, grad_out, grad_grid, grad_keys, shape, stream)),
+      (slice_bwd_atomic_impl<3, true>(src, grid, pad, grad_out, grad_grid, grad_keys, shape, stream)));
+}
+
+int ctb_count_occupied(const float* z, uint64_t n_elements, unsigned long long* count, void* stream) {
+  if (!z || !count) return CTB_ERR_INVALID_ARGUMENT;
+  if (n_elements == 0) return CTB_OK;
+  unsigned blocks = (unsigned)((n_elements + 255) / 256);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  ctb::count_occupied_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, n_elements, count);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,332 @@
+"""torch.autograd.Functions over the C ABI (include/ctb200.h).  PyTorch is plumbing here: it owns the
+device memory and the stream; all arithmetic happens in libctb200.so.
+
+Two families:
+  * reference-API ops (`positions`, `splat`, `slice_`) take / return the reference's tensors
+    (local_coordinate, flattened_index), layers/cloud_transform.py:72-121, :131-180, :190-227;
+  * fused ops (`fused_splat`, `fused_slice`) take the keys through a `PositionsHandle`, never read
+    lc / idx from memory and return grad_keys directly (SURVEY.md rows A1-A7 in four kernels).
+"""
+import ctypes
+import os
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+_MODES = {"auto": None, "atomic": _lib.MODE_ATOMIC, "deterministic": _lib.MODE_DETERMINISTIC}
+
+
+class _Config:
+    """Process-wide switches.  mode: 'auto' (tile kernels when the shape is supported, else the
+    point-stationary atomic kernels), 'atomic', or 'deterministic' (error if unsupported).
+    fused: let Splat / Slice bypass lc / idx when they were produced by our DifferentiablePositions."""
+
+    def __init__(self):
+        self.mode = os.environ.get("CTB_MODE", "auto")
+        self.fused = os.environ.get("CTB_FUSED", "1") != "0"
+
+
+config = _Config()
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cloud_transformers_b200 runs on CUDA tensors only (sm_100a); there is no CPU "
+                               "fallback. Got a tensor on %s." % t.device)
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class Geometry:
+    """tensor_size / heads / dim of a DifferentiableGridModule (cloud_transform.py:29-59)."""
+
+    __slots__ = ("sizes", "heads", "dim", "S", "C")
+
+    def __init__(self, sizes, heads, dim):
+        self.sizes = tuple(int(s) for s in sizes)
+        self.heads = int(heads)
+        self.dim = int(dim)
+        assert self.dim in (2, 3) and len(self.sizes) == self.dim
+        self.S = 1 << self.dim
+        c = 1
+        for s in self.sizes:
+            c *= s
+        self.C = c
+
+    def shape(self, B, F, N):
+        return _lib.make_shape(B, self.heads, F, N, self.dim, self.sizes)
+
+
+def _call(name, *args):
+    lib = _lib.load()
+    _lib.check(name, getattr(lib, name)(*args))
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference-API ops
+class _PositionsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, keys, geom):
+        _require_cuda(keys)
+        k = _f32c(keys)
+        B, HD, N = k.shape
+        assert HD == geom.heads * geom.dim  # cloud_transform.py:84
+        lc = torch.empty((B, geom.heads, geom.S, N), dtype=torch.float32, device=k.device)
+        idx = torch.empty((B, geom.heads, geom.S, N), dtype=torch.int64, device=k.device)
+        with torch.cuda.device(k.device):
+            _call("ctb_positions_fwd", _ptr(k), _ptr(lc), _ptr(idx), ctypes.byref(geom.shape(B, 1, N)), _stream(k))
+        ctx.save_for_backward(k)
+        ctx.geom = geom
+        ctx.mark_non_differentiable(idx)
+        return lc, idx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_lc, _g_idx):
+        (k,) = ctx.saved_tensors
+        geom = ctx.geom
+        B, _, N = k.shape
+        g = _f32c(g_lc)
+        gk = torch.empty_like(k)
+        with torch.cuda.device(k.device):
+            _call("ctb_positions_bwd", _ptr(k), _ptr(g), _ptr(gk), ctypes.byref(geom.shape(B, 1, N)), _stream(k))
+        return gk, None
+
+
+class _SplatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lc, idx, features, pad, geom, reduce):
+        _require_cuda(lc, idx, features, pad)
+        lc_c, f_c, p_c = _f32c(lc), _f32c(features), _f32c(pad)
+        idx_c = idx.contiguous()
+        assert idx_c.dtype == torch.int64
+        B, N = f_c.size(0), f_c.size(-1)
+        F = f_c.size(1) // geom.heads
+        z = torch.empty((B, geom.heads * F) + geom.sizes, dtype=torch.float32, device=f_c.device)
+        arg = torch.empty((B, geom.heads * F, geom.C), dtype=torch.int32, device=f_c.device) \
+            if reduce == _lib.REDUCE_MAX else None
+        with torch.cuda.device(f_c.device):
+            _call("ctb_splat_fwd", _ptr(lc_c), _ptr(idx_c), _ptr(f_c), _ptr(p_c), _ptr(z), _ptr(arg),
+                  ctypes.byref(geom.shape(B, F, N)), reduce, _stream(f_c))
+        ctx.save_for_backward(lc_c, idx_c, f_c, p_c, arg)
+        ctx.geom, ctx.reduce = geom, reduce
+        return z
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gz):
+        lc_c, idx_c, f_c, p_c, arg = ctx.saved_tensors
+        geom = ctx.geom
+        B, N = f_c.size(0), f_c.size(-1)
+        F = f_c.size(1) // geom.heads
+        gz_c = _f32c(gz)
+        gf = torch.empty_like(f_c)
+        glc = torch.empty_like(lc_c)
+        with torch.cuda.device(f_c.device):
+            _call("ctb_splat_bwd", _ptr(lc_c), _ptr(idx_c), _ptr(f_c), _ptr(p_c), _ptr(gz_c), _ptr(arg), _ptr(gf),
+                  _ptr(glc), ctypes.byref(geom.shape(B, F, N)), ctx.reduce, _stream(f_c))
+        return glc, None, gf, None, None, None
+
+
+class _SliceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lc, idx, grid, pad, geom):
+        _require_cuda(lc, idx, grid, pad)
+        lc_c, g_c, p_c = _f32c(lc), _f32c(grid), _f32c(pad)
+        idx_c = idx.contiguous()
+        B, N = lc_c.size(0), lc_c.size(-1)
+        F = g_c.size(1) // geom.heads
+        out = torch.empty((B, geom.heads * F, N), dtype=torch.float32, device=g_c.device)
+        with torch.cuda.device(g_c.device):
+            _call("ctb_slice_fwd", _ptr(lc_c), _ptr(idx_c), _ptr(g_c), _ptr(p_c), _ptr(out),
+                  ctypes.byref(geom.shape(B, F, N)), _stream(g_c))
+        ctx.save_for_backward(lc_c, idx_c, g_c, p_c)
+        ctx.geom = geom
+        ctx.grid_dtype = grid.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        lc_c, idx_c, g_c, p_c = ctx.saved_tensors
+        geom = ctx.geom
+        B, N = lc_c.size(0), lc_c.size(-1)
+        F = g_c.size(1) // geom.heads
+        go_c = _f32c(go)
+        gg = torch.empty_like(g_c)
+        glc = torch.empty_like(lc_c)
+        with torch.cuda.device(g_c.device):
+            _call("ctb_slice_bwd", _ptr(lc_c), _ptr(idx_c), _ptr(g_c), _ptr(p_c), _ptr(go_c), _ptr(gg), _ptr(glc),
+                  ctypes.byref(geom.shape(B, F, N)), _stream(g_c))
+        return glc, None, gg.to(ctx.grid_dtype), None, None
+
+
+def positions(keys, geom):
+    return _PositionsFn.apply(keys, geom)
+
+
+def splat(lc, idx, features, pad, geom, reduce=_lib.REDUCE_MAX):
+    return _SplatFn.apply(lc, idx, features, pad, geom, reduce)
+
+
+def slice_(lc, idx, grid, pad, geom):
+    return _SliceFn.apply(lc, idx, grid, pad, geom)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused ops
+class PositionsHandle:
+    """What DifferentiablePositions knows about one call: the keys tensor (autograd-connected), the
+    geometry, and lazily the cell-sorted plan shared by the Splat forward and the Slice backward."""
+
+    def __init__(self, keys, geom):
+        self.keys = keys
+        self.geom = geom
+        self._keys_c = None
+        self._plan = None
+
+    def keys_c(self):
+        if self._keys_c is None:
+            self._keys_c = _f32c(self.keys.detach())
+        return self._keys_c
+
+    def mode_for(self, op, F, reduce=_lib.REDUCE_MAX):
+        want = config.mode
+        if want not in _MODES:
+            raise ValueError("CTB mode must be one of %s" % sorted(_MODES))
+        if want == "atomic":
+            return _lib.MODE_ATOMIC
+        k = self.keys
+        ok = _lib.load().ctb_deterministic_supported(ctypes.byref(self.geom.shape(k.size(0), F, k.size(-1))), op,
+                                                     reduce)
+        if ok:
+            return _lib.MODE_DETERMINISTIC
+        if want == "deterministic":
+            raise _lib.CtbError("ctb_deterministic_supported", _lib.CTB_ERR_UNSUPPORTED,
+                                "shape not covered by the deterministic tile kernels")
+        return _lib.MODE_ATOMIC
+
+    def plan(self):
+        if self._plan is None:
+            k = self.keys_c()
+            B, _, N = k.shape
+            sh = self.geom.shape(B, 1, N)
+            lib = _lib.load()
+            nbytes = lib.ctb_plan_bytes(ctypes.byref(sh))
+            if nbytes == 0:
+                raise _lib.CtbError("ctb_plan_bytes", _lib.CTB_ERR_UNSUPPORTED, "shape cannot be planned")
+            plan = torch.empty(nbytes, dtype=torch.uint8, device=k.device)
+            with torch.cuda.device(k.device):
+                _call("ctb_plan_build", _ptr(k), _ptr(plan), ctypes.c_size_t(nbytes), ctypes.byref(sh), _stream(k))
+            self._plan = plan
+        return self._plan
+
+
+class _FusedSplatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, keys, features, pad, handle, reduce):
+        _require_cuda(keys, features, pad)
+        geom = handle.geom
+        k, f_c, p_c = handle.keys_c(), _f32c(features), _f32c(pad)
+        B, N = f_c.size(0), f_c.size(-1)
+        F = f_c.size(1) // geom.heads
+        mode = handle.mode_for(_lib.OP_SPLAT_FWD, F, reduce)
+        plan = handle.plan() if mode == _lib.MODE_DETERMINISTIC else None
+        z = torch.empty((B, geom.heads * F) + geom.sizes, dtype=torch.float32, device=f_c.device)
+        arg = torch.empty((B, geom.heads * F, geom.C), dtype=torch.int32, device=f_c.device) \
+            if reduce == _lib.REDUCE_MAX else None
+        with torch.cuda.device(f_c.device):
+            _call("ctb_splat_fwd_keys", _ptr(k), _ptr(f_c), _ptr(p_c), _ptr(z), _ptr(arg),
+                  ctypes.byref(geom.shape(B, F, N)), reduce, mode, _ptr(plan), _stream(f_c))
+        ctx.save_for_backward(k, f_c, p_c, arg)
+        ctx.handle, ctx.reduce = handle, reduce
+        return z
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gz):
+        k, f_c, p_c, arg = ctx.saved_tensors
+        handle = ctx.handle
+        geom = handle.geom
+        B, N = f_c.size(0), f_c.size(-1)
+        F = f_c.size(1) // geom.heads
+        mode = handle.mode_for(_lib.OP_SPLAT_BWD, F, ctx.reduce)
+        gz_c = _f32c(gz)
+        gf = torch.empty_like(f_c)
+        gk = torch.empty_like(k)
+        with torch.cuda.device(f_c.device):
+            _call("ctb_splat_bwd_keys", _ptr(k), _ptr(f_c), _ptr(p_c), _ptr(gz_c), _ptr(arg), _ptr(gf), _ptr(gk),
+                  ctypes.byref(geom.shape(B, F, N)), ctx.reduce, mode, _stream(f_c))
+        return gk, gf, None, None, None
+
+
+class _FusedSliceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, keys, grid, pad, handle):
+        _require_cuda(keys, grid, pad)
+        geom = handle.geom
+        k, g_c, p_c = handle.keys_c(), _f32c(grid), _f32c(pad)
+        B, N = k.size(0), k.size(-1)
+        F = g_c.size(1) // geom.heads
+        mode = handle.mode_for(_lib.OP_SLICE_FWD, F)
+        out = torch.empty((B, geom.heads * F, N), dtype=torch.float32, device=g_c.device)
+        with torch.cuda.device(g_c.device):
+            _call("ctb_slice_fwd_keys", _ptr(k), _ptr(g_c), _ptr(p_c), _ptr(out), ctypes.byref(geom.shape(B, F, N)),
+                  mode, _stream(g_c))
+        ctx.save_for_backward(k, g_c, p_c)
+        ctx.handle = handle
+        ctx.grid_dtype = grid.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        k, g_c, p_c = ctx.saved_tensors
+        handle = ctx.handle
+        geom = handle.geom
+        B, N = k.size(0), k.size(-1)
+        F = g_c.size(1) // geom.heads
+        mode = handle.mode_for(_lib.OP_SLICE_BWD, F)
+        plan = handle.plan() if mode == _lib.MODE_DETERMINISTIC else None
+        go_c = _f32c(go)
+        gg = torch.empty_like(g_c)
+        gk = torch.empty_like(k)
+        with torch.cuda.device(g_c.device):
+            _call("ctb_slice_bwd_keys", _ptr(k), _ptr(g_c), _ptr(p_c), _ptr(go_c), _ptr(gg), _ptr(gk),
+                  ctypes.byref(geom.shape(B, F, N)), mode, _ptr(plan), _stream(g_c))
+        return gk, gg.to(ctx.grid_dtype), None, None
+
+
+def fused_splat(handle, features, pad=None, reduce=_lib.REDUCE_MAX):
+    return _FusedSplatFn.apply(handle.keys, features, pad, handle, reduce)
+
+
+def fused_slice(handle, grid, pad=None):
+    return _FusedSliceFn.apply(handle.keys, grid, pad, handle)
+
+
+def count_occupied(z):
+    """(|z| > 1e-9).sum() as a device tensor (multihead_ct.py:104-105), one pass, no host sync."""
+    _require_cuda(z)
+    z_c = _f32c(z)
+    cnt = torch.zeros(1, dtype=torch.int64, device=z_c.device)
+    with torch.cuda.device(z_c.device):
+        _call("ctb_count_occupied", _ptr(z_c), ctypes.c_uint64(z_c.numel()), _ptr(cnt), _stream(z_c))
+    return cnt[0]

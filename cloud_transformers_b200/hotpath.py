@@ -1,0 +1,107 @@
+"""Allocation-free runner of the fused hot path over the C ABI.
+
+`HotPath` owns the output / workspace buffers of one shape class and issues, per call,
+    plan build (deterministic mode) + Splat forward      ctb_plan_build, ctb_splat_fwd_keys
+    Slice forward                                         ctb_slice_fwd_keys
+    Slice backward (grad_grid, grad_keys)                 ctb_slice_bwd_keys
+    Splat backward (grad_features, grad_keys)             ctb_splat_bwd_keys
+on the current stream with no host synchronisation and no allocation -- the four passes an MHCT block
+(layers/multihead_ct.py:99-107) drives through Splat / Slice in training.  Used by bench.py for the
+device-resident throughput figure and usable for CUDA-graph capture.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .functional import Geometry, _call, _ptr, _stream
+
+
+class HotPath:
+    def __init__(self, tensor_size, heads, dim, B, F, N, device, mode="auto", reduce="max"):
+        sizes = [tensor_size] * dim if isinstance(tensor_size, int) else list(tensor_size)
+        self.geom = Geometry(sizes, heads, dim)
+        self.B, self.F, self.N = B, F, N
+        self.device = torch.device(device)
+        self.reduce = _lib.REDUCE_MAX if reduce == "max" else _lib.REDUCE_SUM
+        self.shape = self.geom.shape(B, F, N)
+        lib = _lib.load()
+        sup = [lib.ctb_deterministic_supported(ctypes.byref(self.shape), op, self.reduce) for op in range(4)]
+        if mode == "deterministic" and not all(sup):
+            raise _lib.CtbError("ctb_deterministic_supported", _lib.CTB_ERR_UNSUPPORTED, "shape not covered")
+        det = mode != "atomic"
+        self.modes = [_lib.MODE_DETERMINISTIC if (det and s) else _lib.MODE_ATOMIC for s in sup]
+        H, C = heads, self.geom.C
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.z = torch.empty((B, H * F) + self.geom.sizes, **f32)
+        self.arg = torch.empty((B, H * F, C), dtype=torch.int32, device=self.device)
+        self.out = torch.empty((B, H * F, N), **f32)
+        self.grad_grid = torch.empty((B, H * F) + self.geom.sizes, **f32)
+        self.grad_keys_slice = torch.empty((B, H * dim, N), **f32)
+        self.grad_keys_splat = torch.empty((B, H * dim, N), **f32)
+        self.grad_feat = torch.empty((B, H * F, N), **f32)
+        self.plan = None
+        if _lib.MODE_DETERMINISTIC in (self.modes[_lib.OP_SPLAT_FWD], self.modes[_lib.OP_SLICE_BWD]):
+            nbytes = lib.ctb_plan_bytes(ctypes.byref(self.shape))
+            self.plan = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._sh = ctypes.byref(self.shape)
+
+    # number of kernel launches (ours) per full fwd+bwd pass, for bench.py's gpu_launches claim
+    def launches_per_pass(self):
+        n = 0
+        n += 2 if self.modes[_lib.OP_SPLAT_FWD] == _lib.MODE_DETERMINISTIC else (2 if self.reduce == 0 else 1)
+        n += 1                                                            # slice fwd
+        n += 2 if self.modes[_lib.OP_SLICE_BWD] == _lib.MODE_DETERMINISTIC else 1
+        n += 1                                                            # splat bwd
+        if self.plan is not None and self.modes[_lib.OP_SPLAT_FWD] != _lib.MODE_DETERMINISTIC:
+            n += 1
+        return n
+
+    def build_plan(self, keys):
+        _call("ctb_plan_build", _ptr(keys), _ptr(self.plan), ctypes.c_size_t(self.plan.numel()), self._sh,
+              _stream(keys))
+
+    def splat_fwd(self, keys, feat, pad=None):
+        if self.plan is not None:
+            self.build_plan(keys)
+        _call("ctb_splat_fwd_keys", _ptr(keys), _ptr(feat), _ptr(pad), _ptr(self.z), _ptr(self.arg), self._sh,
+              self.reduce, self.modes[_lib.OP_SPLAT_FWD], _ptr(self.plan), _stream(keys))
+        return self.z
+
+    def slice_fwd(self, keys, grid, pad=None):
+        _call("ctb_slice_fwd_keys", _ptr(keys), _ptr(grid), _ptr(pad), _ptr(self.out), self._sh,
+              self.modes[_lib.OP_SLICE_FWD], _stream(keys))
+        return self.out
+
+    def slice_bwd(self, keys, grid, grad_out, pad=None):
+        _call("ctb_slice_bwd_keys", _ptr(keys), _ptr(grid), _ptr(pad), _ptr(grad_out), _ptr(self.grad_grid),
+              _ptr(self.grad_keys_slice), self._sh, self.modes[_lib.OP_SLICE_BWD], _ptr(self.plan), _stream(keys))
+        return self.grad_grid, self.grad_keys_slice
+
+    def splat_bwd(self, keys, feat, grad_z, pad=None):
+        _call("ctb_splat_bwd_keys", _ptr(keys), _ptr(feat), _ptr(pad), _ptr(grad_z), _ptr(self.arg),
+              _ptr(self.grad_feat), _ptr(self.grad_keys_splat), self._sh, self.reduce,
+              self.modes[_lib.OP_SPLAT_BWD], _stream(keys))
+        return self.grad_feat, self.grad_keys_splat
+
+    def fwd_bwd(self, keys, feat, conv, grad_out, grad_z, pad=None):
+        """One pass of the hot path; `conv` stands for the convolved grid (the conv itself is outside the
+        metric), `grad_z` for the gradient the conv backward hands to Splat."""
+        self.splat_fwd(keys, feat, pad)
+        self.slice_fwd(keys, conv, pad)
+        self.slice_bwd(keys, conv, grad_out, pad)
+        self.splat_bwd(keys, feat, grad_z, pad)
+
+
+def algorithmic_bytes(N, dim, F, C, e=4):
+    """minimal HBM bytes per (batch, head) unit, per pass and in total (reduce = max)."""
+    d = dim
+    per = {
+        "splat_fwd": N * (4 * d + e * F) + e * F * C,
+        "slice_fwd": N * (4 * d + e * F) + e * F * C,
+        "slice_bwd": N * (8 * d + e * F) + 2 * e * F * C,
+        "splat_bwd": N * (8 * d + 2 * e * F) + 2 * e * F * C,
+    }
+    per["total"] = sum(per.values())
+    assert per["total"] == N * (24 * d + 5 * e * F) + 6 * e * F * C
+    return per

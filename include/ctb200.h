@@ -1,0 +1,141 @@
+/* ctb200.h -- C ABI of libctb200.so: the B200 (sm_100a) Splat / Slice hot path of Cloud Transformers.
+ *
+ * Drop-in boundary for the reference's L1 operators (all citations relative to the reference repo):
+ *   layers/cloud_transform.py:62-121  DifferentiablePositions.forward  (+ layers/utils.py:100-186)
+ *   layers/cloud_transform.py:124-180 Splat.forward   (torch_scatter.scatter_max call at :171-173)
+ *   layers/cloud_transform.py:183-227 Slice.forward   (torch.gather call at :216-218)
+ * and the autograd backward of each.
+ *
+ * Conventions
+ *   - Plain C: raw DEVICE pointers, sizes, and a `void* stream` (a cudaStream_t; NULL = legacy default
+ *     stream).  No torch types.  The library allocates nothing that outlives a call, keeps no state
+ *     between calls, never synchronises the device and only enqueues work on the given stream, so it
+ *     is safe to call from PyTorch's autograd thread and alongside DDP's side streams.
+ *   - All tensors are dense, row-major (C-contiguous) with the reference's shapes:
+ *       keys      f32 [B, H*dim, N]      head-major then axis (cloud_transform.py:89)
+ *       lc        f32 [B, H, S, N]       S = 2^dim corner weights ("local_coordinate")
+ *       idx       i64 [B, H, S, N]       flattened cell index of each corner ("flattened_index")
+ *       features  f32 [B, H*F, N]
+ *       pad       f32 [B, N] or NULL     "pts_padding" (cloud_transform.py:158-159, :224-225)
+ *       grid      f32 [B, H*F, C]        C = prod(size); NCHW / NCDHW exactly as the reference returns
+ *       arg       i32 [B, H*F, C]        winner e = s*N + n of every cell, -1 where nothing beat the 0 floor
+ *   - Every entry returns 0 on success or a negative ctb_status; it never throws and never exits.
+ *   - Corner order: bit0 of s is +1 on grid axis 0 (the slowest axis), bit1 axis 1, bit2 axis 2
+ *     (layers/utils.py:103-110, :161-164); flat index = x*W1*W2 + y*W2 + z (cloud_transform.py:113-119).
+ */
+#ifndef CTB200_H
+#define CTB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTB_VERSION 100 /* major*100 + minor */
+
+typedef enum ctb_status {
+  CTB_OK = 0,
+  CTB_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, non-positive size, dim not in {2,3}, size < 2 ... */
+  CTB_ERR_UNSUPPORTED = -2,      /* shape outside what the kernels support (e.g. S*N >= 2^31) */
+  CTB_ERR_CUDA = -3,             /* a CUDA runtime call failed; see ctb_last_cuda_error() */
+  CTB_ERR_WORKSPACE = -4         /* workspace missing or too small */
+} ctb_status;
+
+/* reduce operator of Splat: MAX is the reference (scatter_max onto a zero grid => implicit 0 floor,
+ * cloud_transform.py:164-173); SUM is the scatter-add variant named by the north star. */
+typedef enum ctb_reduce { CTB_REDUCE_MAX = 0, CTB_REDUCE_SUM = 1 } ctb_reduce;
+
+/* algorithm selector for the scatters (Splat forward, Slice backward):
+ *   ATOMIC        point-stationary, L2 atomics (red.global); values of MAX are order independent and
+ *                 the arg winner is resolved with a min-e pass, so Splat-max is reproducible; the float
+ *                 sums of Slice backward / Splat-sum depend on atomic arrival order.
+ *   DETERMINISTIC cell-stationary: points are sorted by cell (needs a plan, see ctb_plan_build) and
+ *                 every cell is reduced by its single owner in a fixed order with plain stores --
+ *                 no atomics, bit-identical from run to run. */
+typedef enum ctb_mode { CTB_MODE_ATOMIC = 0, CTB_MODE_DETERMINISTIC = 1 } ctb_mode;
+
+/* geometry of one call.  size[2] is ignored when dim == 2. */
+typedef struct ctb_shape {
+  int32_t B;       /* batch of clouds */
+  int32_t H;       /* heads */
+  int32_t F;       /* feature channels per head (ignored by the positions entries) */
+  int32_t N;       /* points per cloud */
+  int32_t dim;     /* 2 or 3 */
+  int32_t size[3]; /* grid extent per axis, each >= 2 (tensor_size, cloud_transform.py:41-46) */
+} ctb_shape;
+
+int ctb_version(void);
+const char* ctb_strerror(int status);
+/* cudaError_t of the last failing CUDA call made by this library on the calling thread (0 if none). */
+int ctb_last_cuda_error(void);
+
+/* ---- A1 / A7: DifferentiablePositions (cloud_transform.py:72-121, utils.py:100-186) ------------- */
+/* keys -> lc, idx.  Bit-exact replay of clamp(+-(1-1e-7)) -> +1 -> *(W-1)/2 -> floor -> corner products. */
+int ctb_positions_fwd(const float* keys, float* lc, int64_t* idx, const ctb_shape* shape, void* stream);
+/* grad_lc -> grad_keys: identity through GradientBalancing (cloud_transform.py:21-23, no (W-1)/2
+ * factor), zero where the key was clamped (:91). */
+int ctb_positions_bwd(const float* keys, const float* grad_lc, float* grad_keys, const ctb_shape* shape,
+                      void* stream);
+
+/* ---- reference-API operators: lc / idx are tensors handed in by the caller ---------------------- */
+/* A2+A3  Splat.forward (cloud_transform.py:131-180): z[b,h,f,c] = max(0, max_{(s,n): idx=c} feat*pad*lc)
+ * (or the plain sum for CTB_REDUCE_SUM).  z and arg are fully overwritten; arg may be NULL for SUM. */
+int ctb_splat_fwd(const float* lc, const int64_t* idx, const float* features, const float* pad, float* z,
+                  int32_t* arg, const ctb_shape* shape, int reduce, void* stream);
+/* A6  Splat backward (ScatterMax::backward + MulBackward): grad_z -> grad_features, grad_lc. */
+int ctb_splat_bwd(const float* lc, const int64_t* idx, const float* features, const float* pad,
+                  const float* grad_z, const int32_t* arg, float* grad_features, float* grad_lc,
+                  const ctb_shape* shape, int reduce, void* stream);
+/* A4  Slice.forward (cloud_transform.py:190-227): out[b,h,f,n] = pad * sum_s lc * grid[b,h,f,idx]. */
+int ctb_slice_fwd(const float* lc, const int64_t* idx, const float* grid, const float* pad, float* out,
+                  const ctb_shape* shape, void* stream);
+/* A5  Slice backward (gather backward = scatter-add): grad_out -> grad_grid (fully overwritten), grad_lc. */
+int ctb_slice_bwd(const float* lc, const int64_t* idx, const float* grid, const float* pad,
+                  const float* grad_out, float* grad_grid, float* grad_lc, const ctb_shape* shape,
+                  void* stream);
+
+/* ---- fused operators: positions are recomputed from keys inside every kernel -------------------- */
+/* Same results as the reference-API operators fed with ctb_positions_fwd's outputs (identical device
+ * code computes the positions), but lc / idx are never materialised and the backward entries emit
+ * grad_keys directly (A7 folded in).
+ *
+ * mode = CTB_MODE_ATOMIC        point-stationary kernels, any shape.
+ * mode = CTB_MODE_DETERMINISTIC cell-stationary shared-memory tile kernels; the two scatters
+ *        (ctb_splat_fwd_keys, grad_grid of ctb_slice_bwd_keys) need the `plan` built by
+ *        ctb_plan_build from the same keys; returns CTB_ERR_UNSUPPORTED for shapes the tile kernels
+ *        do not cover (ask ctb_deterministic_supported first) -- there is no silent fallback. */
+typedef enum ctb_op {
+  CTB_OP_SPLAT_FWD = 0,
+  CTB_OP_SPLAT_BWD = 1,
+  CTB_OP_SLICE_FWD = 2,
+  CTB_OP_SLICE_BWD = 3
+} ctb_op;
+/* 1 if `op` can run in CTB_MODE_DETERMINISTIC on this shape (reduce only matters for the Splat ops). */
+int ctb_deterministic_supported(const ctb_shape* shape, int op, int reduce);
+
+/* bytes of the plan for this shape, 0 if the shape cannot be planned. */
+size_t ctb_plan_bytes(const ctb_shape* shape);
+/* sort the S*N (point, corner) entries of every (b, h) unit by destination cell. */
+int ctb_plan_build(const float* keys, void* plan, size_t plan_bytes, const ctb_shape* shape, void* stream);
+
+int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pad, float* z, int32_t* arg,
+                       const ctb_shape* shape, int reduce, int mode, const void* plan, void* stream);
+int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pad, const float* grad_z,
+                       const int32_t* arg, float* grad_features, float* grad_keys, const ctb_shape* shape,
+                       int reduce, int mode, void* stream);
+int ctb_slice_fwd_keys(const float* keys, const float* grid, const float* pad, float* out,
+                       const ctb_shape* shape, int mode, void* stream);
+int ctb_slice_bwd_keys(const float* keys, const float* grid, const float* pad, const float* grad_out,
+                       float* grad_grid, float* grad_keys, const ctb_shape* shape, int mode,
+                       const void* plan, void* stream);
+
+/* A9  occupancy statistic of MultiHead blocks (layers/multihead_ct.py:104-105): count of |z| > 1e-9
+ * accumulated into *count (u64, device memory, caller zeroes it). */
+int ctb_count_occupied(const float* z, uint64_t n_elements, unsigned long long* count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTB200_H */

@@ -1,0 +1,105 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every symbol include/ctb200.h declares, argument
+validation works without touching a GPU, and the host-side mirror keeps the reference's interface."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ctb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctb_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cloud_transformers_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 17
+    for name in declared:
+        assert hasattr(lib, name), "libctb200.so does not export %s" % name
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes signatures out of sync with the header"
+    assert lib.ctb_version() == 100
+    assert lib.ctb_strerror(-2) == b"unsupported shape"
+
+
+def test_argument_validation_without_gpu():
+    from cloud_transformers_b200 import _lib
+    lib = _lib.load()
+    sh = _lib.make_shape(2, 4, 4, 128, 2, (16, 16))
+    # NULL pointers are rejected before any CUDA call
+    assert lib.ctb_positions_fwd(None, None, None, ctypes.byref(sh), None) == _lib.CTB_ERR_INVALID_ARGUMENT
+    assert lib.ctb_slice_fwd_keys(None, None, None, None, ctypes.byref(sh), 0, None) == _lib.CTB_ERR_INVALID_ARGUMENT
+    bad = _lib.make_shape(2, 4, 4, 128, 4, (16, 16))
+    assert lib.ctb_positions_fwd(None, None, None, ctypes.byref(bad), None) == _lib.CTB_ERR_INVALID_ARGUMENT
+    tiny = _lib.make_shape(2, 4, 4, 128, 2, (1, 16))
+    assert lib.ctb_plan_bytes(ctypes.byref(tiny)) == 0
+    # plan sizing and the support query are pure host logic
+    assert lib.ctb_plan_bytes(ctypes.byref(sh)) >= 2 * 4 * 4 * 128 * 8
+    assert lib.ctb_deterministic_supported(ctypes.byref(sh), _lib.OP_SPLAT_FWD, _lib.REDUCE_MAX) == 1
+    huge = _lib.make_shape(1, 1, 4, 1 << 18, 2, (256, 256))
+    assert lib.ctb_deterministic_supported(ctypes.byref(huge), _lib.OP_SPLAT_FWD, _lib.REDUCE_MAX) == 0
+    assert lib.ctb_plan_bytes(ctypes.byref(huge)) == 0
+    for dim, W, F, N in [(2, 128, 4, 2048), (3, 32, 4, 2048), (2, 64, 16, 2048), (3, 16, 16, 2048), (2, 16, 16, 2048),
+                         (3, 8, 32, 2048), (3, 32, 4, 4096)]:
+        s = _lib.make_shape(32, 16, F, N, dim, (W,) * dim)
+        for op in range(4):
+            assert lib.ctb_deterministic_supported(ctypes.byref(s), op, _lib.REDUCE_MAX) == 1, (dim, W, F, N, op)
+
+
+def test_module_interface_matches_reference():
+    """ctor defaults, attributes, buffer names (cloud_transform.py:29-59) -- checkpoints must load strictly."""
+    import cloud_transformers_b200 as ctb
+    for cls in (ctb.DifferentiablePositions, ctb.Splat, ctb.Slice):
+        m = cls()
+        assert (m.dim, m.heads, m.tensor_size, m.spread_size, m.eps) == (3, 4, [20, 20, 20], 8, 1e-7)
+        assert list(m.state_dict().keys()) == ["tensor_mod"]
+        assert m.tensor_mod.shape == (1, 3, 1) and m.tensor_mod.dtype == torch.float32
+        m2 = cls(tensor_size=(6, 10), heads=2, dim=2)
+        assert m2.tensor_size == (6, 10) and m2.spread_size == 4
+        with pytest.raises(AssertionError):
+            cls(tensor_size=(6, 10), dim=3)
+    from oracle import reference_loader as RL
+    if RL.available():
+        ct, _, _ = RL.load_reference_layers()
+        for name in ("DifferentiablePositions", "Splat", "Slice"):
+            ref = getattr(ct, name)(tensor_size=16, heads=4, dim=2)
+            ours = getattr(ctb, name)(tensor_size=16, heads=4, dim=2)
+            assert ref.state_dict().keys() == ours.state_dict().keys()
+            ours.load_state_dict(ref.state_dict(), strict=True)
+            for attr in ("dim", "heads", "tensor_size", "spread_size", "eps"):
+                assert getattr(ref, attr) == getattr(ours, attr)
+
+
+def test_cpu_tensors_fail_loudly():
+    """No CPU fallback: the product path refuses CPU tensors instead of silently computing on the host."""
+    import cloud_transformers_b200 as ctb
+    dp = ctb.DifferentiablePositions(tensor_size=8, heads=2, dim=2)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        dp(torch.zeros(1, 4, 16))
+    sp = ctb.Splat(tensor_size=8, heads=2, dim=2)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        sp(torch.zeros(1, 2, 4, 16), torch.zeros(1, 2, 4, 16, dtype=torch.int64), torch.zeros(1, 4, 16))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from cloud_transformers_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError, match="no CPU / PyTorch fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_oracle():
+    """Only tests/, smoke() and bench.py's CPU-baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "cloud_transformers_b200")
+    pat = re.compile(r"^\s*(from|import)\s+\.*oracle\b|#include\s+[\"<].*oracle", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                assert not pat.search(open(os.path.join(dirpath, f)).read()), f

@@ -1,0 +1,335 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI via the host-side mirror, against the oracle
+on the same seeded inputs, against the golden fixtures minted from the reference, and -- at BASELINE's
+full sizes -- through size-independent properties.
+
+Tolerances (north star): cell indices, corner weights and the Splat-max grid are BIT-EXACT; everything
+that sums floats is within rel 1e-5 (absolute floor 1e-5 * max|ref|).
+"""
+import numpy as np
+import pytest
+import torch
+
+import cloud_transformers_b200 as ctb
+from cloud_transformers_b200 import _lib, functional as CF
+from oracle import ct_numpy as O
+from tests.util import GOLDEN_CASES, assert_close, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+MODES = ["atomic", "deterministic"]
+
+
+@pytest.fixture(autouse=True)
+def _mode_reset():
+    yield
+    ctb.config.mode = "auto"
+    ctb.config.fused = True
+
+
+def t(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def n(x):
+    return x.detach().cpu().numpy()
+
+
+def run_block(keys, feat, pad, conv, go, gz, W, H, dim, fused=True, mode="auto", reduce="max"):
+    """positions -> Splat -> (given conv grid) -> Slice, forward and both backwards, like an MHCT block."""
+    ctb.config.mode = mode
+    ctb.config.fused = fused
+    dp = ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim).to(DEV)
+    sp = ctb.Splat(tensor_size=W, heads=H, dim=dim, reduce=reduce).to(DEV)
+    sl = ctb.Slice(tensor_size=W, heads=H, dim=dim).to(DEV)
+    k = t(keys).requires_grad_(True)
+    f = t(feat).requires_grad_(True)
+    p = t(pad)
+    c = t(conv).requires_grad_(True) if conv is not None else None
+    lc, idx = dp(k)
+    z = sp(lc, idx, f, p)
+    if c is None:
+        c = torch.randn_like(z).requires_grad_(True)
+    out = sl(lc, idx, c, p)
+    res = dict(lc=n(lc), idx=n(idx), z=n(z), out=n(out), conv=n(c))
+    if go is not None:
+        (out * t(go)).sum().backward(retain_graph=True)
+        res["gk_slice"] = n(k.grad)
+        res["gconv"] = n(c.grad)
+        k.grad = None
+    if gz is not None:
+        (z * t(gz)).sum().backward()
+        res["gk_splat"] = n(k.grad)
+        res["gfeat"] = n(f.grad)
+    torch.cuda.synchronize()
+    return res
+
+
+def oracle_block(keys, feat, pad, conv, go, gz, W, H, dim, reduce="max"):
+    lc, idx = O.positions_fwd(keys, W, H, dim)
+    z, arg = O.splat_fwd(lc, idx, feat, W, H, dim, pad, reduce=reduce, return_arg=True)
+    out = O.slice_fwd(lc, idx, conv, H, pad)
+    gg, glc = O.slice_bwd(lc, idx, conv, go, H, pad)
+    gf, glc2 = O.splat_bwd(lc, idx, feat, gz, arg, W, H, dim, pad, reduce=reduce)
+    return dict(lc=lc, idx=idx, z=z, out=out, gconv=gg, gk_slice=O.positions_bwd(keys, glc, W, H, dim), gfeat=gf,
+                gk_splat=O.positions_bwd(keys, glc2, W, H, dim), arg=arg)
+
+
+def compare(res, ref, what, exact_z=True):
+    assert np.array_equal(res["idx"], ref["idx"]), what + ": flattened_index must be bit-exact"
+    assert np.array_equal(res["lc"], ref["lc"]), what + ": local_coordinate must be bit-exact"
+    if exact_z:
+        assert np.array_equal(res["z"], ref["z"]), what + ": Splat-max grid must be bit-exact"
+    else:
+        assert_close(res["z"], ref["z"], what + " z")
+    for k in ("out", "gconv", "gk_slice", "gfeat", "gk_splat"):
+        assert_close(res[k], ref[k], what + " " + k)
+
+
+# --- golden fixtures minted from the reference -------------------------------------------------------
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_against_reference_golden(golden, name, fused, mode):
+    dim, W, H, F, N, B = GOLDEN_CASES[name]
+    g = {k.split("/", 1)[1]: golden[k] for k in golden.files if k.startswith(name + "/")}
+    res = run_block(g["keys"], g["feat"], g.get("pad"), g["conv"], g["go"], g["gz"], W, H, dim, fused, mode)
+    ref = dict(g)
+    ref["idx"] = g["idx"].astype(np.int64)
+    compare(res, ref, "%s fused=%s %s" % (name, fused, mode))
+
+
+def test_adversarial_indices_bit_exact(golden):
+    ak = golden["adv/keys"]
+    for dim in (2, 3):
+        for W in ((8, 16, 32, 64, 128, 256) if dim == 2 else (8, 16, 32, 64)):
+            keys = np.tile(ak[None, None, :], (1, dim, 1)).astype(np.float32)
+            dp = ctb.DifferentiablePositions(tensor_size=W, heads=1, dim=dim)
+            lc, idx = dp(t(keys))
+            assert np.array_equal(n(idx), golden["adv/idx_d%d_w%d" % (dim, W)].astype(np.int64))
+            assert np.array_equal(n(lc), golden["adv/lc_d%d_w%d" % (dim, W)])
+
+
+def test_indices_bit_exact_on_1e7_keys():
+    rng = np.random.default_rng(0)
+    for dim, W in [(2, 128), (3, 32)]:
+        N = 1 << 20
+        keys = np.tanh(rng.standard_normal((5 if dim == 2 else 4, dim, N)) * 1.5).astype(np.float32)
+        dp = ctb.DifferentiablePositions(tensor_size=W, heads=1, dim=dim)
+        lc, idx = dp(t(keys))
+        lc_o, idx_o = O.positions_fwd(keys, W, 1, dim)
+        assert np.array_equal(n(idx), idx_o) and np.array_equal(n(lc), lc_o)
+
+
+# --- oracle on seeded inputs: every model shape class at reduced batch -------------------------------
+SHAPES = [
+    # dim, W, H, F, N, B
+    (2, 128, 4, 4, 2048, 2), (3, 32, 4, 4, 2048, 2), (2, 64, 4, 16, 2048, 1), (3, 16, 4, 16, 2048, 1),
+    (2, 16, 4, 16, 2048, 1), (3, 8, 4, 32, 2048, 1), (2, 64, 16, 4, 2048, 2), (3, 32, 2, 4, 4096, 1),
+    (2, (24, 40), 3, 5, 777, 2), (3, (6, 9, 12), 2, 3, 1000, 2), (2, 8, 2, 1, 1, 1), (3, 4, 1, 2, 5, 3),
+]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "d%d_w%s_h%d_f%d_n%d_b%d" % s)
+def test_against_oracle(shape, mode):
+    dim, W, H, F, N, B = shape
+    keys, feat, pad = make_inputs(hash(shape) % 1000, B, H, dim, F, N, pad=(N % 2 == 1))
+    C = int(np.prod(O._sizes(W, dim)))
+    rng = np.random.default_rng(5)
+    conv = rng.standard_normal((B, H * F) + tuple(O._sizes(W, dim))).astype(np.float32)
+    go = rng.standard_normal((B, H * F, N)).astype(np.float32)
+    gz = rng.standard_normal(conv.shape).astype(np.float32)
+    ref = oracle_block(keys, feat, pad, conv, go, gz, W, H, dim)
+    for fused in (True, False):
+        res = run_block(keys, feat, pad, conv, go, gz, W, H, dim, fused, mode)
+        compare(res, ref, "fused=%s %s" % (fused, mode))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("dist", ["uniform", "onecell"])
+def test_collision_extremes(dist, mode):
+    """uniform keys and the adversarial all-points-in-one-cell case."""
+    for dim, W, H, F, N, B in [(2, 32, 2, 4, 1024, 1), (3, 8, 2, 8, 1024, 1)]:
+        keys, feat, pad = make_inputs(11, B, H, dim, F, N, dist=dist)
+        rng = np.random.default_rng(6)
+        conv = rng.standard_normal((B, H * F) + (W,) * dim).astype(np.float32)
+        go = rng.standard_normal((B, H * F, N)).astype(np.float32)
+        gz = rng.standard_normal(conv.shape).astype(np.float32)
+        ref = oracle_block(keys, feat, pad, conv, go, gz, W, H, dim)
+        res = run_block(keys, feat, pad, conv, go, gz, W, H, dim, True, mode)
+        compare(res, ref, "%s %s d%d" % (dist, mode, dim))
+
+
+def test_edge_keys_and_zero_floor():
+    """keys exactly +-1 / beyond, all-negative features (nothing beats the 0 floor), fully padded cloud."""
+    dim, W, H, F, N, B = 2, 16, 2, 3, 64, 2
+    keys, feat, _ = make_inputs(2, B, H, dim, F, N)
+    keys[0, :, :8] = np.array([1.0, -1.0, 2.0, -3.0, 0.99999994, -0.99999994, 0.0, 1.0], dtype=np.float32)
+    feat[0] = -np.abs(feat[0])
+    pad = np.ones((B, N), dtype=np.float32)
+    pad[1] = 0.0
+    for mode in MODES:
+        ctb.config.mode = mode
+        dp = ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim)
+        sp = ctb.Splat(tensor_size=W, heads=H, dim=dim)
+        k = t(keys).requires_grad_(True)
+        f = t(feat).requires_grad_(True)
+        lc, idx = dp(k)
+        z = sp(lc, idx, f, t(pad))
+        assert float(z.abs().max()) == 0.0          # batch 0 all negative, batch 1 fully padded
+        assert int(idx.min()) >= 0 and int(idx.max()) < W * W
+        z.sum().backward()
+        assert float(f.grad.abs().max()) == 0.0 and float(k.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_tie_breaking_first_winner(mode):
+    """Duplicate points => exact ties; the gradient goes to exactly one winner, the lowest e = s*N + n
+    (torch-scatter CPU rule)."""
+    dim, W, H, F, N, B = 2, 8, 1, 2, 32, 1
+    keys, feat, _ = make_inputs(4, B, H, dim, F, N)
+    keys[:, :, 16:] = keys[:, :, :16]
+    feat[:, :, 16:] = feat[:, :, :16]
+    rng = np.random.default_rng(3)
+    conv = rng.standard_normal((B, H * F, W, W)).astype(np.float32)
+    go = rng.standard_normal((B, H * F, N)).astype(np.float32)
+    gz = rng.standard_normal(conv.shape).astype(np.float32)
+    ref = oracle_block(keys, feat, None, conv, go, gz, W, H, dim)
+    res = run_block(keys, feat, None, conv, go, gz, W, H, dim, True, mode)
+    compare(res, ref, "ties " + mode)
+    assert np.abs(res["gfeat"][:, :, 16:]).max() == 0.0   # the duplicates (higher n) never win
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_reduce_sum_variant(mode):
+    for dim, W, H, F, N, B in [(2, 16, 2, 4, 512, 2), (3, 8, 2, 4, 300, 1)]:
+        keys, feat, pad = make_inputs(9, B, H, dim, F, N, pad=True)
+        rng = np.random.default_rng(8)
+        conv = rng.standard_normal((B, H * F) + (W,) * dim).astype(np.float32)
+        go = rng.standard_normal((B, H * F, N)).astype(np.float32)
+        gz = rng.standard_normal(conv.shape).astype(np.float32)
+        ref = oracle_block(keys, feat, pad, conv, go, gz, W, H, dim, reduce="sum")
+        if mode == "deterministic":
+            # Splat-sum backward has no tile kernel: exercise the scatter only
+            ctb.config.mode = mode
+            h = CF.PositionsHandle(t(keys), CF.Geometry(O._sizes(W, dim), H, dim))
+            z = CF.fused_splat(h, t(feat), t(pad), _lib.REDUCE_SUM)
+            assert np.array_equal(n(z), ref["z"]), "deterministic sum accumulates in ascending e like the oracle"
+        else:
+            res = run_block(keys, feat, pad, conv, go, gz, W, H, dim, True, mode, reduce="sum")
+            compare(res, ref, "sum " + mode, exact_z=False)
+
+
+def test_deterministic_mode_is_bit_reproducible_and_matches_atomic():
+    dim, W, H, F, N, B = 3, 16, 4, 16, 2048, 2
+    keys, feat, _ = make_inputs(21, B, H, dim, F, N)
+    rng = np.random.default_rng(2)
+    conv = rng.standard_normal((B, H * F, W, W, W)).astype(np.float32)
+    go = rng.standard_normal((B, H * F, N)).astype(np.float32)
+    gz = rng.standard_normal(conv.shape).astype(np.float32)
+    runs = [run_block(keys, feat, None, conv, go, gz, W, H, dim, True, "deterministic") for _ in range(3)]
+    for r in runs[1:]:
+        for k in ("z", "out", "gconv", "gk_slice", "gfeat", "gk_splat"):
+            assert np.array_equal(r[k], runs[0][k]), "deterministic mode must be bit-identical run to run: " + k
+    at = run_block(keys, feat, None, conv, go, gz, W, H, dim, True, "atomic")
+    assert np.array_equal(at["z"], runs[0]["z"]) and np.array_equal(at["out"], runs[0]["out"])
+    assert np.array_equal(at["gfeat"], runs[0]["gfeat"])
+    assert_close(at["gconv"], runs[0]["gconv"], "atomic vs deterministic grad grid")
+
+
+def test_arg_identical_across_algorithms():
+    """The winner index written by the atomic (max + min-e pass) and the sorted kernels is the same tensor."""
+    for dim, W, H, F, N, B in [(2, 32, 4, 4, 2048, 2), (3, 8, 2, 8, 1024, 1)]:
+        keys, feat, pad = make_inputs(13, B, H, dim, F, N, pad=True)
+        keys[:, :, N // 2:] = keys[:, :, :N // 2]      # force ties
+        feat[:, :, N // 2:] = feat[:, :, :N // 2]
+        geom = CF.Geometry(O._sizes(W, dim), H, dim)
+        sh = geom.shape(B, F, N)
+        args = []
+        feat_d, pad_d = t(feat), t(pad)
+        for mode in (_lib.MODE_ATOMIC, _lib.MODE_DETERMINISTIC):
+            h = CF.PositionsHandle(t(keys), geom)
+            z = torch.empty((B, H * F, geom.C), device=DEV)
+            arg = torch.empty((B, H * F, geom.C), dtype=torch.int32, device=DEV)
+            plan = h.plan() if mode == _lib.MODE_DETERMINISTIC else None
+            import ctypes
+            CF._call("ctb_splat_fwd_keys", CF._ptr(h.keys_c()), CF._ptr(feat_d), CF._ptr(pad_d), CF._ptr(z),
+                     CF._ptr(arg), ctypes.byref(sh), 0, mode, CF._ptr(plan), CF._stream(z))
+            torch.cuda.synchronize()
+            args.append((n(z), n(arg)))
+        assert np.array_equal(args[0][0], args[1][0]) and np.array_equal(args[0][1], args[1][1])
+        lc, idx = O.positions_fwd(keys, W, H, dim)
+        z_o, arg_o = O.splat_fwd(lc, idx, feat, W, H, dim, pad, return_arg=True)
+        arg_o = np.where(arg_o == (1 << dim) * N, -1, arg_o).reshape(B, H * F, geom.C)
+        assert np.array_equal(args[0][1], arg_o.astype(np.int32))
+
+
+# --- full BASELINE sizes: size-independent properties -------------------------------------------------
+FULL = [(2, 128, 16, 4, 2048, 32), (3, 32, 16, 4, 2048, 32), (2, 64, 16, 16, 2048, 32), (3, 16, 16, 16, 2048, 32),
+        (2, 16, 16, 16, 2048, 32), (3, 8, 16, 32, 2048, 32), (3, 32, 16, 4, 4096, 8)]
+
+
+@pytest.mark.parametrize("shape", FULL, ids=lambda s: "d%d_w%d_h%d_f%d_n%d_b%d" % s)
+def test_full_size_properties(shape):
+    dim, W, H, F, N, B = shape
+    g = torch.Generator(device=DEV).manual_seed(1)
+    keys = torch.tanh(torch.randn(B, H * dim, N, device=DEV, generator=g))
+    feat = torch.randn(B, H * F, N, device=DEV, generator=g)
+    outs = {}
+    for mode in MODES:
+        ctb.config.mode = mode
+        dp = ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim)
+        sp = ctb.Splat(tensor_size=W, heads=H, dim=dim)
+        sl = ctb.Slice(tensor_size=W, heads=H, dim=dim)
+        k = keys.clone().requires_grad_(True)
+        f = feat.clone().requires_grad_(True)
+        lc, idx = dp(k)
+        z = sp(lc, idx, f)
+        out = sl(lc, idx, z)
+        gsum = torch.autograd.grad(out.sum(), [k, f], retain_graph=True)
+        # Slice is linear in the grid: slice(2 z) == 2 slice(z)
+        out2 = sl(lc, idx, 2.0 * z)
+        assert torch.allclose(out2, 2.0 * out, rtol=1e-5, atol=1e-6)
+        # weights of a point sum to 1 => slicing a constant grid returns the constant
+        ones = sl(lc, idx, torch.ones_like(z))
+        assert float((ones - 1).abs().max()) < 1e-5
+        # z >= 0 (zero floor) and every positive cell is attained by some point: z <= max positive feature
+        assert float(z.min()) >= 0.0
+        assert float(z.max()) <= float(feat.clamp(min=0).max()) + 1e-6
+        # index range
+        assert int(idx.min()) >= 0 and int(idx.max()) < W ** dim
+        outs[mode] = (z, out, gsum)
+    za, oa, ga = outs["atomic"]
+    zd, od, gd = outs["deterministic"]
+    assert torch.equal(za, zd), "Splat-max grid: atomic and deterministic kernels must agree bit for bit"
+    assert torch.equal(oa, od)
+    assert torch.allclose(ga[1], gd[1], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(ga[0], gd[0], rtol=1e-4, atol=1e-4 * float(ga[0].abs().max()))
+    # cross-check one (b, h) unit of the full-size run against the oracle
+    kb = n(keys[:1, :dim]); fb = n(feat[:1, :F])
+    lc_o, idx_o = O.positions_fwd(kb, W, 1, dim)
+    z_o = O.splat_fwd(lc_o, idx_o, fb, W, 1, dim)
+    assert np.array_equal(n(zd[:1, :F]), z_o)
+
+
+def test_occupancy_count():
+    z = torch.randn(3, 8, 16, 16, device=DEV)
+    z[z.abs() < 0.5] = 0
+    assert int(CF.count_occupied(z)) == int((z.abs() > 1e-9).sum())
+
+
+def test_non_default_stream_and_noncontiguous_inputs():
+    dim, W, H, F, N, B = 2, 16, 2, 4, 256, 2
+    keys, feat, _ = make_inputs(1, B, H, dim, F, N)
+    ref = run_block(keys, feat, None, None, None, None, W, H, dim)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        dp = ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim)
+        sp = ctb.Splat(tensor_size=W, heads=H, dim=dim)
+        k = t(np.ascontiguousarray(keys.transpose(0, 2, 1))).transpose(1, 2)   # non-contiguous view
+        f = t(np.ascontiguousarray(feat.transpose(0, 2, 1))).transpose(1, 2)
+        lc, idx = dp(k)
+        z = sp(lc, idx, f)
+    s.synchronize()
+    assert np.array_equal(n(z), ref["z"])
