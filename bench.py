@@ -374,7 +374,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("CTB_MODE", "auto"), choices=["auto", "atomic", "deterministic"])
+    ap.add_argument("--mode", default=os.environ.get("CTB_MODE", "auto"), choices=["auto", "atomic", "tile", "deterministic"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -18,7 +18,7 @@ CTB_ERR_CUDA = -3
 CTB_ERR_WORKSPACE = -4
 
 REDUCE_MAX, REDUCE_SUM = 0, 1
-MODE_ATOMIC, MODE_DETERMINISTIC = 0, 1
+MODE_ATOMIC, MODE_DETERMINISTIC, MODE_TILE = 0, 1, 2
 OP_SPLAT_FWD, OP_SPLAT_BWD, OP_SLICE_FWD, OP_SLICE_BWD = 0, 1, 2, 3
 
 
@@ -48,7 +48,7 @@ SIGNATURES = {
     "ctb_splat_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _SH, _I, _P]),
     "ctb_slice_fwd": (_I, [_P, _P, _P, _P, _P, _SH, _P]),
     "ctb_slice_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _SH, _P]),
-    "ctb_deterministic_supported": (_I, [_SH, _I, _I]),
+    "ctb_mode_supported": (_I, [_SH, _I, _I, _I]),
     "ctb_plan_bytes": (ctypes.c_size_t, [_SH]),
     "ctb_plan_build": (_I, [_P, _P, ctypes.c_size_t, _SH, _P]),
     "ctb_splat_fwd_keys": (_I, [_P, _P, _P, _P, _P, _SH, _I, _I, _P, _P]),

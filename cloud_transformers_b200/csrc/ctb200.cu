@@ -5,6 +5,7 @@
 #include "ctb_positions.cuh"
 #include "ctb_generic.cuh"
 #include "ctb_sorted.cuh"
+#include "ctb_tile_scatter.cuh"
 
 namespace {
 
@@ -245,17 +246,24 @@ int ctb_slice_bwd(const float* lc, const int64_t* idx, const float* grid, const 
       (slice_bwd_atomic_impl<3, false>(src, grid, pad, grad_out, grad_grid, grad_lc, shape, stream)));
 }
 
-int ctb_deterministic_supported(const ctb_shape* shape, int op, int reduce) {
+int ctb_mode_supported(const ctb_shape* shape, int op, int reduce, int mode) {
   if (check_shape(shape, true)) return 0;
+  if (mode == CTB_MODE_ATOMIC) return 1;
+  if (mode != CTB_MODE_TILE && mode != CTB_MODE_DETERMINISTIC) return 0;
   const bool sum = reduce == CTB_REDUCE_SUM;
+  const bool det = mode == CTB_MODE_DETERMINISTIC;
   ctb::ScatterConfig sc;
+  ctb::TileScatterConfig tc;
   ctb::GatherConfig gc;
   switch (op) {
-    case CTB_OP_SPLAT_FWD: return ctb::plan_supported(shape) && ctb::scatter_config(shape, sum, &sc);
+    case CTB_OP_SPLAT_FWD:
+      return det ? (ctb::plan_supported(shape) && ctb::scatter_config(shape, sum, &sc))
+                 : ctb::tile_scatter_config(shape, sum, !sum, &tc);
     case CTB_OP_SPLAT_BWD: return sum ? 0 : ctb::gather_config(shape, ctb::GATHER_SPLAT_BWD, &gc);
     case CTB_OP_SLICE_FWD: return ctb::gather_config(shape, ctb::GATHER_SLICE_FWD, &gc);
     case CTB_OP_SLICE_BWD:
-      return ctb::plan_supported(shape) && ctb::scatter_config(shape, true, &sc) &&
+      return (det ? (ctb::plan_supported(shape) && ctb::scatter_config(shape, true, &sc))
+                  : ctb::tile_scatter_config(shape, true, false, &tc)) &&
              ctb::gather_config(shape, ctb::GATHER_SLICE_BWD_KEYS, &gc);
     default: return 0;
   }
@@ -291,6 +299,12 @@ int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pa
                            ? ctb::sorted_scatter<2>(plan, features, pad, z, arg, shape, sum, (cudaStream_t)stream)
                            : ctb::sorted_scatter<3>(plan, features, pad, z, arg, shape, sum, (cudaStream_t)stream));
   }
+  if (mode == CTB_MODE_TILE) {
+    const bool sum = reduce == CTB_REDUCE_SUM;
+    return cuda_status(shape->dim == 2
+                           ? ctb::tile_scatter<2>(keys, features, pad, z, sum ? nullptr : arg, shape, sum, (cudaStream_t)stream)
+                           : ctb::tile_scatter<3>(keys, features, pad, z, sum ? nullptr : arg, shape, sum, (cudaStream_t)stream));
+  }
   if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;
   ctb::PointSource src{keys, nullptr, nullptr};
   return CTB_DISPATCH_DIM(shape,
@@ -306,7 +320,7 @@ int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pa
   if (!keys || !features || !grad_z || !grad_features || !grad_keys) return CTB_ERR_INVALID_ARGUMENT;
   if (reduce != CTB_REDUCE_MAX && reduce != CTB_REDUCE_SUM) return CTB_ERR_INVALID_ARGUMENT;
   if (reduce == CTB_REDUCE_MAX && !arg) return CTB_ERR_INVALID_ARGUMENT;
-  if (mode == CTB_MODE_DETERMINISTIC) {
+  if (mode == CTB_MODE_DETERMINISTIC || mode == CTB_MODE_TILE) {
     if (reduce != CTB_REDUCE_MAX) return CTB_ERR_UNSUPPORTED;
     return cuda_status(shape->dim == 2
                            ? (ctb::tile_gather<2, ctb::GATHER_SPLAT_BWD>(keys, grad_z, arg, features, pad, grad_features,
@@ -327,7 +341,7 @@ int ctb_slice_fwd_keys(const float* keys, const float* grid, const float* pad, f
   int st = check_shape(shape, true);
   if (st) return st;
   if (!keys || !grid || !out) return CTB_ERR_INVALID_ARGUMENT;
-  if (mode == CTB_MODE_DETERMINISTIC)
+  if (mode == CTB_MODE_DETERMINISTIC || mode == CTB_MODE_TILE)
     return cuda_status(shape->dim == 2
                            ? (ctb::tile_gather<2, ctb::GATHER_SLICE_FWD>(keys, grid, nullptr, nullptr, pad, out, nullptr,
                                                                         shape, (cudaStream_t)stream))
@@ -345,13 +359,19 @@ int ctb_slice_bwd_keys(const float* keys, const float* grid, const float* pad, c
   int st = check_shape(shape, true);
   if (st) return st;
   if (!keys || !grid || !grad_out || !grad_grid || !grad_keys) return CTB_ERR_INVALID_ARGUMENT;
-  if (mode == CTB_MODE_DETERMINISTIC) {
-    if (!plan) return CTB_ERR_WORKSPACE;
-    if (!ctb_deterministic_supported(shape, CTB_OP_SLICE_BWD, CTB_REDUCE_SUM)) return CTB_ERR_UNSUPPORTED;
-    // grad_grid: cell-stationary scatter-add of grad_out * pad (the Splat-sum kernel) ...
-    st = cuda_status(shape->dim == 2
-                         ? ctb::sorted_scatter<2>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream)
-                         : ctb::sorted_scatter<3>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream));
+  if (mode == CTB_MODE_DETERMINISTIC || mode == CTB_MODE_TILE) {
+    if (!ctb_mode_supported(shape, CTB_OP_SLICE_BWD, CTB_REDUCE_SUM, mode)) return CTB_ERR_UNSUPPORTED;
+    // grad_grid: scatter-add of grad_out * pad (the Splat-sum kernel of the mode) ...
+    if (mode == CTB_MODE_DETERMINISTIC) {
+      if (!plan) return CTB_ERR_WORKSPACE;
+      st = cuda_status(shape->dim == 2
+                           ? ctb::sorted_scatter<2>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream)
+                           : ctb::sorted_scatter<3>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream));
+    } else {
+      st = cuda_status(shape->dim == 2
+                           ? ctb::tile_scatter<2>(keys, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream)
+                           : ctb::tile_scatter<3>(keys, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream));
+    }
     if (st) return st;
     // ... and grad_keys: tile gather against the convolved grid.
     return cuda_status(shape->dim == 2

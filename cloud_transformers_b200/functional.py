@@ -15,12 +15,12 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib
 
-_MODES = {"auto": None, "atomic": _lib.MODE_ATOMIC, "deterministic": _lib.MODE_DETERMINISTIC}
+_MODES = {"auto": None, "atomic": _lib.MODE_ATOMIC, "tile": _lib.MODE_TILE, "deterministic": _lib.MODE_DETERMINISTIC}
 
 
 class _Config:
-    """Process-wide switches.  mode: 'auto' (tile kernels when the shape is supported, else the
-    point-stationary atomic kernels), 'atomic', or 'deterministic' (error if unsupported).
+    """Process-wide switches.  mode: 'auto' (shared-memory tile kernels when the shape is supported, else
+    the point-stationary L2-atomic kernels), 'atomic', 'tile' or 'deterministic' (error if unsupported).
     fused: let Splat / Slice bypass lc / idx when they were produced by our DifferentiablePositions."""
 
     def __init__(self):
@@ -214,13 +214,13 @@ class PositionsHandle:
         if want == "atomic":
             return _lib.MODE_ATOMIC
         k = self.keys
-        ok = _lib.load().ctb_deterministic_supported(ctypes.byref(self.geom.shape(k.size(0), F, k.size(-1))), op,
-                                                     reduce)
+        mode = _lib.MODE_DETERMINISTIC if want == "deterministic" else _lib.MODE_TILE
+        ok = _lib.load().ctb_mode_supported(ctypes.byref(self.geom.shape(k.size(0), F, k.size(-1))), op, reduce, mode)
         if ok:
-            return _lib.MODE_DETERMINISTIC
-        if want == "deterministic":
-            raise _lib.CtbError("ctb_deterministic_supported", _lib.CTB_ERR_UNSUPPORTED,
-                                "shape not covered by the deterministic tile kernels")
+            return mode
+        if want != "auto":
+            raise _lib.CtbError("ctb_mode_supported", _lib.CTB_ERR_UNSUPPORTED,
+                                "shape not covered by the %s kernels" % want)
         return _lib.MODE_ATOMIC
 
     def plan(self):

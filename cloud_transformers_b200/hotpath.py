@@ -26,11 +26,12 @@ class HotPath:
         self.reduce = _lib.REDUCE_MAX if reduce == "max" else _lib.REDUCE_SUM
         self.shape = self.geom.shape(B, F, N)
         lib = _lib.load()
-        sup = [lib.ctb_deterministic_supported(ctypes.byref(self.shape), op, self.reduce) for op in range(4)]
-        if mode == "deterministic" and not all(sup):
-            raise _lib.CtbError("ctb_deterministic_supported", _lib.CTB_ERR_UNSUPPORTED, "shape not covered")
-        det = mode != "atomic"
-        self.modes = [_lib.MODE_DETERMINISTIC if (det and s) else _lib.MODE_ATOMIC for s in sup]
+        want = {"auto": _lib.MODE_TILE, "tile": _lib.MODE_TILE, "deterministic": _lib.MODE_DETERMINISTIC,
+                "atomic": _lib.MODE_ATOMIC}[mode]
+        sup = [lib.ctb_mode_supported(ctypes.byref(self.shape), op, self.reduce, want) for op in range(4)]
+        if mode in ("tile", "deterministic") and not all(sup):
+            raise _lib.CtbError("ctb_mode_supported", _lib.CTB_ERR_UNSUPPORTED, "shape not covered")
+        self.modes = [want if s else _lib.MODE_ATOMIC for s in sup]
         H, C = heads, self.geom.C
         f32 = dict(dtype=torch.float32, device=self.device)
         self.z = torch.empty((B, H * F) + self.geom.sizes, **f32)
@@ -48,13 +49,12 @@ class HotPath:
 
     # number of kernel launches (ours) per full fwd+bwd pass, for bench.py's gpu_launches claim
     def launches_per_pass(self):
-        n = 0
-        n += 2 if self.modes[_lib.OP_SPLAT_FWD] == _lib.MODE_DETERMINISTIC else (2 if self.reduce == 0 else 1)
+        m_sf, m_sb = self.modes[_lib.OP_SPLAT_FWD], self.modes[_lib.OP_SLICE_BWD]
+        n = 1 if self.plan is not None else 0                             # plan build
+        n += 1 if m_sf != _lib.MODE_ATOMIC else (2 if self.reduce == 0 else 1)   # splat fwd
         n += 1                                                            # slice fwd
-        n += 2 if self.modes[_lib.OP_SLICE_BWD] == _lib.MODE_DETERMINISTIC else 1
+        n += 1 if m_sb == _lib.MODE_ATOMIC else 2                         # slice bwd: scatter + gather
         n += 1                                                            # splat bwd
-        if self.plan is not None and self.modes[_lib.OP_SPLAT_FWD] != _lib.MODE_DETERMINISTIC:
-            n += 1
         return n
 
     def build_plan(self, keys):

@@ -47,14 +47,18 @@ typedef enum ctb_status {
  * cloud_transform.py:164-173); SUM is the scatter-add variant named by the north star. */
 typedef enum ctb_reduce { CTB_REDUCE_MAX = 0, CTB_REDUCE_SUM = 1 } ctb_reduce;
 
-/* algorithm selector for the scatters (Splat forward, Slice backward):
- *   ATOMIC        point-stationary, L2 atomics (red.global); values of MAX are order independent and
- *                 the arg winner is resolved with a min-e pass, so Splat-max is reproducible; the float
- *                 sums of Slice backward / Splat-sum depend on atomic arrival order.
- *   DETERMINISTIC cell-stationary: points are sorted by cell (needs a plan, see ctb_plan_build) and
- *                 every cell is reduced by its single owner in a fixed order with plain stores --
- *                 no atomics, bit-identical from run to run. */
-typedef enum ctb_mode { CTB_MODE_ATOMIC = 0, CTB_MODE_DETERMINISTIC = 1 } ctb_mode;
+/* algorithm selector of the fused entries:
+ *   ATOMIC        point-stationary kernels on the NCHW grid in L2: red.global atomics for the scatters,
+ *                 direct loads for the gathers.  Any shape.  Splat-max is reproducible (max is order
+ *                 independent, the arg winner is resolved by a min-e pass); float sums are not.
+ *   TILE          CTA-owned shared-memory tiles of the grid: scatters accumulate with native
+ *                 shared-memory atomics and store every cell once (no zero-fill, no L2 atomics), gathers
+ *                 stage the slab with coalesced 16-byte loads.  Splat-max is reproducible; the float
+ *                 sums (Slice backward grad_grid, Splat-sum) depend on warp scheduling.  The fast path.
+ *   DETERMINISTIC as TILE, but the two scatters walk entries sorted by destination cell (needs a plan,
+ *                 see ctb_plan_build): every cell is reduced by one owner in ascending e = s*N + n with
+ *                 plain stores -- no atomics anywhere, bit-identical from run to run. */
+typedef enum ctb_mode { CTB_MODE_ATOMIC = 0, CTB_MODE_DETERMINISTIC = 1, CTB_MODE_TILE = 2 } ctb_mode;
 
 /* geometry of one call.  size[2] is ignored when dim == 2. */
 typedef struct ctb_shape {
@@ -101,19 +105,18 @@ int ctb_slice_bwd(const float* lc, const int64_t* idx, const float* grid, const 
  * code computes the positions), but lc / idx are never materialised and the backward entries emit
  * grad_keys directly (A7 folded in).
  *
- * mode = CTB_MODE_ATOMIC        point-stationary kernels, any shape.
- * mode = CTB_MODE_DETERMINISTIC cell-stationary shared-memory tile kernels; the two scatters
- *        (ctb_splat_fwd_keys, grad_grid of ctb_slice_bwd_keys) need the `plan` built by
- *        ctb_plan_build from the same keys; returns CTB_ERR_UNSUPPORTED for shapes the tile kernels
- *        do not cover (ask ctb_deterministic_supported first) -- there is no silent fallback. */
+ * mode: see ctb_mode.  CTB_MODE_DETERMINISTIC needs the `plan` built by ctb_plan_build from the same
+ *        keys for the two scatters (ctb_splat_fwd_keys, grad_grid of ctb_slice_bwd_keys).  TILE and
+ *        DETERMINISTIC return CTB_ERR_UNSUPPORTED for shapes the tile kernels do not cover (ask
+ *        ctb_mode_supported first) -- there is no silent fallback inside the library. */
 typedef enum ctb_op {
   CTB_OP_SPLAT_FWD = 0,
   CTB_OP_SPLAT_BWD = 1,
   CTB_OP_SLICE_FWD = 2,
   CTB_OP_SLICE_BWD = 3
 } ctb_op;
-/* 1 if `op` can run in CTB_MODE_DETERMINISTIC on this shape (reduce only matters for the Splat ops). */
-int ctb_deterministic_supported(const ctb_shape* shape, int op, int reduce);
+/* 1 if `op` can run in `mode` on this shape (reduce only matters for the Splat ops). */
+int ctb_mode_supported(const ctb_shape* shape, int op, int reduce, int mode);
 
 /* bytes of the plan for this shape, 0 if the shape cannot be planned. */
 size_t ctb_plan_bytes(const ctb_shape* shape);

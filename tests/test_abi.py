@@ -41,15 +41,17 @@ def test_argument_validation_without_gpu():
     assert lib.ctb_plan_bytes(ctypes.byref(tiny)) == 0
     # plan sizing and the support query are pure host logic
     assert lib.ctb_plan_bytes(ctypes.byref(sh)) >= 2 * 4 * 4 * 128 * 8
-    assert lib.ctb_deterministic_supported(ctypes.byref(sh), _lib.OP_SPLAT_FWD, _lib.REDUCE_MAX) == 1
+    assert lib.ctb_mode_supported(ctypes.byref(sh), _lib.OP_SPLAT_FWD, _lib.REDUCE_MAX, _lib.MODE_DETERMINISTIC) == 1
     huge = _lib.make_shape(1, 1, 4, 1 << 18, 2, (256, 256))
-    assert lib.ctb_deterministic_supported(ctypes.byref(huge), _lib.OP_SPLAT_FWD, _lib.REDUCE_MAX) == 0
+    assert lib.ctb_mode_supported(ctypes.byref(huge), _lib.OP_SPLAT_FWD, _lib.REDUCE_MAX, _lib.MODE_DETERMINISTIC) == 0
+    assert lib.ctb_mode_supported(ctypes.byref(huge), _lib.OP_SPLAT_FWD, _lib.REDUCE_MAX, _lib.MODE_ATOMIC) == 1
     assert lib.ctb_plan_bytes(ctypes.byref(huge)) == 0
     for dim, W, F, N in [(2, 128, 4, 2048), (3, 32, 4, 2048), (2, 64, 16, 2048), (3, 16, 16, 2048), (2, 16, 16, 2048),
                          (3, 8, 32, 2048), (3, 32, 4, 4096)]:
         s = _lib.make_shape(32, 16, F, N, dim, (W,) * dim)
         for op in range(4):
-            assert lib.ctb_deterministic_supported(ctypes.byref(s), op, _lib.REDUCE_MAX) == 1, (dim, W, F, N, op)
+            for mode in (_lib.MODE_TILE, _lib.MODE_DETERMINISTIC):
+                assert lib.ctb_mode_supported(ctypes.byref(s), op, _lib.REDUCE_MAX, mode) == 1, (dim, W, F, N, op, mode)
 
 
 def test_module_interface_matches_reference():

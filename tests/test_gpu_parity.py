@@ -17,7 +17,7 @@ from tests.util import GOLDEN_CASES, assert_close, make_inputs
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
-MODES = ["atomic", "deterministic"]
+MODES = ["atomic", "tile", "deterministic"]
 
 
 @pytest.fixture(autouse=True)
@@ -210,12 +210,16 @@ def test_reduce_sum_variant(mode):
         go = rng.standard_normal((B, H * F, N)).astype(np.float32)
         gz = rng.standard_normal(conv.shape).astype(np.float32)
         ref = oracle_block(keys, feat, pad, conv, go, gz, W, H, dim, reduce="sum")
-        if mode == "deterministic":
+        if mode in ("deterministic", "tile"):
             # Splat-sum backward has no tile kernel: exercise the scatter only
             ctb.config.mode = mode
             h = CF.PositionsHandle(t(keys), CF.Geometry(O._sizes(W, dim), H, dim))
-            z = CF.fused_splat(h, t(feat), t(pad), _lib.REDUCE_SUM)
-            assert np.array_equal(n(z), ref["z"]), "deterministic sum accumulates in ascending e like the oracle"
+            with torch.no_grad():
+                z = CF.fused_splat(h, t(feat), t(pad), _lib.REDUCE_SUM)
+            if mode == "deterministic":
+                assert np.array_equal(n(z), ref["z"]), "deterministic sum accumulates in ascending e like the oracle"
+            else:
+                assert_close(n(z), ref["z"], "tile sum")
         else:
             res = run_block(keys, feat, pad, conv, go, gz, W, H, dim, True, mode, reduce="sum")
             compare(res, ref, "sum " + mode, exact_z=False)
@@ -232,10 +236,16 @@ def test_deterministic_mode_is_bit_reproducible_and_matches_atomic():
     for r in runs[1:]:
         for k in ("z", "out", "gconv", "gk_slice", "gfeat", "gk_splat"):
             assert np.array_equal(r[k], runs[0][k]), "deterministic mode must be bit-identical run to run: " + k
-    at = run_block(keys, feat, None, conv, go, gz, W, H, dim, True, "atomic")
-    assert np.array_equal(at["z"], runs[0]["z"]) and np.array_equal(at["out"], runs[0]["out"])
-    assert np.array_equal(at["gfeat"], runs[0]["gfeat"])
-    assert_close(at["gconv"], runs[0]["gconv"], "atomic vs deterministic grad grid")
+    for other in ("atomic", "tile"):
+        at = run_block(keys, feat, None, conv, go, gz, W, H, dim, True, other)
+        assert np.array_equal(at["z"], runs[0]["z"]) and np.array_equal(at["out"], runs[0]["out"])
+        assert np.array_equal(at["gfeat"], runs[0]["gfeat"])
+        assert_close(at["gconv"], runs[0]["gconv"], other + " vs deterministic grad grid")
+    # Splat-max of the tile mode needs no sort to be reproducible (max + min-e are order independent)
+    t1 = run_block(keys, feat, None, conv, go, gz, W, H, dim, True, "tile")
+    t2 = run_block(keys, feat, None, conv, go, gz, W, H, dim, True, "tile")
+    for k in ("z", "out", "gfeat", "gk_splat", "gk_slice"):
+        assert np.array_equal(t1[k], t2[k]), k
 
 
 def test_arg_identical_across_algorithms():
@@ -248,7 +258,7 @@ def test_arg_identical_across_algorithms():
         sh = geom.shape(B, F, N)
         args = []
         feat_d, pad_d = t(feat), t(pad)
-        for mode in (_lib.MODE_ATOMIC, _lib.MODE_DETERMINISTIC):
+        for mode in (_lib.MODE_ATOMIC, _lib.MODE_DETERMINISTIC, _lib.MODE_TILE):
             h = CF.PositionsHandle(t(keys), geom)
             z = torch.empty((B, H * F, geom.C), device=DEV)
             arg = torch.empty((B, H * F, geom.C), dtype=torch.int32, device=DEV)
@@ -258,7 +268,8 @@ def test_arg_identical_across_algorithms():
                      CF._ptr(arg), ctypes.byref(sh), 0, mode, CF._ptr(plan), CF._stream(z))
             torch.cuda.synchronize()
             args.append((n(z), n(arg)))
-        assert np.array_equal(args[0][0], args[1][0]) and np.array_equal(args[0][1], args[1][1])
+        for other in args[1:]:
+            assert np.array_equal(args[0][0], other[0]) and np.array_equal(args[0][1], other[1])
         lc, idx = O.positions_fwd(keys, W, H, dim)
         z_o, arg_o = O.splat_fwd(lc, idx, feat, W, H, dim, pad, return_arg=True)
         arg_o = np.where(arg_o == (1 << dim) * N, -1, arg_o).reshape(B, H * F, geom.C)
@@ -300,12 +311,13 @@ def test_full_size_properties(shape):
         # index range
         assert int(idx.min()) >= 0 and int(idx.max()) < W ** dim
         outs[mode] = (z, out, gsum)
-    za, oa, ga = outs["atomic"]
     zd, od, gd = outs["deterministic"]
-    assert torch.equal(za, zd), "Splat-max grid: atomic and deterministic kernels must agree bit for bit"
-    assert torch.equal(oa, od)
-    assert torch.allclose(ga[1], gd[1], rtol=1e-4, atol=1e-5)
-    assert torch.allclose(ga[0], gd[0], rtol=1e-4, atol=1e-4 * float(ga[0].abs().max()))
+    for other in ("atomic", "tile"):
+        za, oa, ga = outs[other]
+        assert torch.equal(za, zd), "Splat-max grid: all three algorithms must agree bit for bit"
+        assert torch.equal(oa, od)
+        assert torch.allclose(ga[1], gd[1], rtol=1e-4, atol=1e-5)
+        assert torch.allclose(ga[0], gd[0], rtol=1e-4, atol=1e-4 * float(ga[0].abs().max()))
     # cross-check one (b, h) unit of the full-size run against the oracle
     kb = n(keys[:1, :dim]); fb = n(feat[:1, :F])
     lc_o, idx_o = O.positions_fwd(kb, W, 1, dim)
