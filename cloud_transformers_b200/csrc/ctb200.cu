@@ -5,7 +5,7 @@
 #include "ctb_positions.cuh"
 #include "ctb_generic.cuh"
 #include "ctb_sorted.cuh"
-#include "ctb_tile_scatter.cuh"
+#include "ctb_tile.cuh"
 
 namespace {
 
@@ -253,8 +253,8 @@ int ctb_mode_supported(const ctb_shape* shape, int op, int reduce, int mode) {
   const bool sum = reduce == CTB_REDUCE_SUM;
   const bool det = mode == CTB_MODE_DETERMINISTIC;
   ctb::ScatterConfig sc;
-  ctb::TileScatterConfig tc;
-  ctb::GatherConfig gc;
+  ctb::TileConfig tc;
+  ctb::TileConfig gc;
   switch (op) {
     case CTB_OP_SPLAT_FWD:
       return det ? (ctb::plan_supported(shape) && ctb::scatter_config(shape, sum, &sc))

@@ -1,4 +1,5 @@
-// ctb_sorted.cuh -- cell-stationary (CTB_MODE_DETERMINISTIC) kernels: plan build, tile scatter, tile gather.
+// ctb_sorted.cuh -- cell-stationary (CTB_MODE_DETERMINISTIC) scatter: plan build + sorted-entry tile scatter.
+// (The gathers of this mode are the tile gathers of ctb_tile.cuh, which are deterministic by construction.)
 //
 // Idea.  A (batch, head) unit owns its own grid slab, so the S*N (point, corner) "entries" of a unit are
 // sorted ONCE by destination cell (plan_kernel, bitonic sort in shared memory).  After that
@@ -22,7 +23,6 @@ namespace ctb {
 
 constexpr int kPlanThreads = 1024;
 constexpr int kScatterThreads = 512;
-constexpr int kGatherThreads = 512;
 constexpr int kScatterChunk = 2048;          // entries staged per step
 constexpr int kMaxSortEntries = 32768;       // S*N padded to a power of two must fit shared memory
 constexpr int kSmemBudgetTwoCtas = 110 * 1024;
@@ -363,209 +363,6 @@ cudaError_t sorted_scatter(const void* plan, const float* feat, const float* pad
   }
 #undef CTB_SC
   return cudaErrorNotSupported;
-}
-
-// ---- tile gather --------------------------------------------------------------------------------------
-// One CTA = one unit.  Loops over channel groups (FG planes) and slabs of R rows (+1 halo row); every
-// point is resolved in the single slab that holds its base row, against the shared-memory tile.
-enum GatherMode { GATHER_SLICE_FWD = 0, GATHER_SLICE_BWD_KEYS = 1, GATHER_SPLAT_BWD = 2 };
-
-template <int D, int MODE, int PPT, bool VEC4>
-__global__ void __launch_bounds__(kGatherThreads, 2)
-gather_kernel(const float* __restrict__ keys, const float* __restrict__ t1, const int* __restrict__ t2,
-              const float* __restrict__ in, const float* __restrict__ pad, float* __restrict__ out,
-              float* __restrict__ grad_keys, Grid<D> g, int H, int F, int N, int FG, int R) {
-  constexpr int S = 1 << D;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int stride0 = g.stride[0];
-  const int W0 = g.W[0];
-  const int tile_cells = (R + 1) * stride0;
-  float* s1 = (float*)smem_raw;                         // [FG][tile_cells]
-  int* s2 = (int*)(s1 + (size_t)FG * tile_cells);       // [FG][tile_cells]  (SPLAT_BWD: arg)
-  const int unit = blockIdx.x;
-  const float* ku = keys + (size_t)unit * D * N;
-  const float* pu = pad ? pad + (size_t)(unit / H) * N : nullptr;
-
-  float gk[PPT][D];
-#pragma unroll
-  for (int k = 0; k < PPT; ++k)
-#pragma unroll
-    for (int a = 0; a < D; ++a) gk[k][a] = 0.0f;
-
-  for (int f0 = 0; f0 < F; f0 += FG) {
-    const int fg = min(FG, F - f0);
-    for (int x0 = 0; x0 < W0 - 1; x0 += R) {
-      // tile rows [x0, xe): base rows [x0, x0 + R) plus the +1 corner row
-      const int xe = min(x0 + R + 1, W0);
-      const int cell0 = x0 * stride0;
-      const int ncell = (xe - x0) * stride0;
-      if constexpr (VEC4) {
-        const int n4 = ncell >> 2;
-        for (int i = threadIdx.x; i < fg * n4; i += kGatherThreads) {
-          const int f = i / n4, r = i - f * n4;
-          reinterpret_cast<float4*>(s1 + (size_t)f * tile_cells)[r] =
-              __ldcs(reinterpret_cast<const float4*>(t1 + ((size_t)unit * F + f0 + f) * g.C + cell0) + r);
-          if constexpr (MODE == GATHER_SPLAT_BWD)
-            reinterpret_cast<int4*>(s2 + (size_t)f * tile_cells)[r] =
-                __ldcs(reinterpret_cast<const int4*>(t2 + ((size_t)unit * F + f0 + f) * g.C + cell0) + r);
-        }
-      } else {
-        for (int i = threadIdx.x; i < fg * ncell; i += kGatherThreads) {
-          const int f = i / ncell, r = i - f * ncell;
-          s1[(size_t)f * tile_cells + r] = __ldg(t1 + ((size_t)unit * F + f0 + f) * g.C + cell0 + r);
-          if constexpr (MODE == GATHER_SPLAT_BWD)
-            s2[(size_t)f * tile_cells + r] = __ldg(t2 + ((size_t)unit * F + f0 + f) * g.C + cell0 + r);
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        const int n = threadIdx.x + k * kGatherThreads;
-        if (n >= N) continue;
-        const Pos<D> p = point_pos<D>(ku, n, N, g);
-        const int bx = p.c0;
-        if (bx < x0 || bx >= x0 + R) continue;
-        const float pd = pu ? __ldg(pu + n) : 1.0f;
-        float w[S];
-        int lc[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          w[s] = corner_weight<D>(p, s);
-          lc[s] = p.base + corner_offset<D>(g, s) - cell0;
-        }
-        float gw[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) gw[s] = 0.0f;
-        for (int f = 0; f < fg; ++f) {
-          const float* tf = s1 + (size_t)f * tile_cells;
-          const size_t po = ((size_t)unit * F + f0 + f) * N + n;
-          if constexpr (MODE == GATHER_SLICE_FWD) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const float t = CTB_FMUL(tf[lc[s]], w[s]);
-              acc = (s == 0) ? t : CTB_FADD(acc, t);
-            }
-            if (pu) acc = CTB_FMUL(acc, pd);
-            out[po] = acc;
-          } else if constexpr (MODE == GATHER_SLICE_BWD_KEYS) {
-            float go = __ldg(in + po);
-            if (pu) go *= pd;
-#pragma unroll
-            for (int s = 0; s < S; ++s) gw[s] = fmaf(tf[lc[s]], go, gw[s]);
-          } else {
-            const int* af = s2 + (size_t)f * tile_cells;
-            float ft = __ldg(in + po);
-            if (pu) ft *= pd;
-            float gf = 0.0f;
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              if (af[lc[s]] == s * N + n) {
-                const float gz = tf[lc[s]];
-                gf = fmaf(gz, w[s], gf);
-                gw[s] = fmaf(gz, ft, gw[s]);
-              }
-            }
-            if (pu) gf *= pd;
-            out[po] = gf;
-          }
-        }
-        if constexpr (MODE != GATHER_SLICE_FWD) {
-          float part[D];
-          weight_grad_to_key_grad<D>(p, gw, part);
-#pragma unroll
-          for (int a = 0; a < D; ++a) gk[k][a] += part[a];
-        }
-      }
-      __syncthreads();
-    }
-  }
-  if constexpr (MODE != GATHER_SLICE_FWD) {
-#pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-      const int n = threadIdx.x + k * kGatherThreads;
-      if (n >= N) continue;
-#pragma unroll
-      for (int a = 0; a < D; ++a) grad_keys[((size_t)unit * D + a) * N + n] = gk[k][a];
-    }
-  }
-}
-
-struct GatherConfig {
-  int FG, R, PPT;
-  size_t smem;
-};
-
-inline bool gather_config(const ctb_shape* s, int mode, GatherConfig* out) {
-  const int stride0 = s->dim == 2 ? s->size[1] : s->size[1] * s->size[2];
-  const int W0 = s->size[0];
-  const size_t per_cell = mode == GATHER_SPLAT_BWD ? 8 : 4;
-  const int ppt = (s->N + kGatherThreads - 1) / kGatherThreads;
-  if (ppt > 8) return false;
-  out->PPT = ppt <= 1 ? 1 : (ppt <= 2 ? 2 : (ppt <= 4 ? 4 : 8));
-  const size_t plane = (size_t)W0 * stride0 * per_cell;
-  // (1) whole planes, as many channels per tile as fit while two CTAs still share an SM
-  if (plane <= (size_t)kSmemBudgetTwoCtas) {
-    int FG = (int)((size_t)kSmemBudgetTwoCtas / plane);
-    if (FG > s->F) FG = s->F;
-    const int groups = (s->F + FG - 1) / FG;
-    FG = (s->F + groups - 1) / groups;
-    out->FG = FG;
-    out->R = W0 - 1;
-    out->smem = (size_t)FG * plane;
-    return true;
-  }
-  // (2) one plane at a time in balanced slabs of R base rows (+1 halo row)
-  for (int pass = 0; pass < 2; ++pass) {
-    const size_t budget = pass == 0 ? kSmemBudgetTwoCtas : kSmemBudgetMax;
-    int R = (int)(budget / ((size_t)stride0 * per_cell)) - 1;
-    if (R < 1) continue;
-    if (R > W0 - 1) R = W0 - 1;
-    const int slabs = (W0 - 1 + R - 1) / R;
-    R = (W0 - 1 + slabs - 1) / slabs;
-    out->FG = 1;
-    out->R = R;
-    out->smem = (size_t)(R + 1) * stride0 * per_cell;
-    return true;
-  }
-  return false;
-}
-
-template <int D, int MODE, int PPT>
-cudaError_t launch_gather(const float* keys, const float* t1, const int* t2, const float* in, const float* pad,
-                          float* out, float* grad_keys, const ctb_shape* s, const GatherConfig& c,
-                          cudaStream_t stream) {
-  const Grid<D> g = make_grid<D>(s->size);
-  const bool vec4 = (g.C % 4 == 0) && (g.stride[0] % 4 == 0) && ((reinterpret_cast<uintptr_t>(t1) & 15) == 0) &&
-                    (MODE != GATHER_SPLAT_BWD || (reinterpret_cast<uintptr_t>(t2) & 15) == 0);
-  cudaError_t e;
-  if (vec4) {
-    e = cudaFuncSetAttribute(gather_kernel<D, MODE, PPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)c.smem);
-    if (e != cudaSuccess) return e;
-    gather_kernel<D, MODE, PPT, true><<<(unsigned)(s->B * s->H), kGatherThreads, c.smem, stream>>>(
-        keys, t1, t2, in, pad, out, grad_keys, g, s->H, s->F, s->N, c.FG, c.R);
-  } else {
-    e = cudaFuncSetAttribute(gather_kernel<D, MODE, PPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)c.smem);
-    if (e != cudaSuccess) return e;
-    gather_kernel<D, MODE, PPT, false><<<(unsigned)(s->B * s->H), kGatherThreads, c.smem, stream>>>(
-        keys, t1, t2, in, pad, out, grad_keys, g, s->H, s->F, s->N, c.FG, c.R);
-  }
-  return cudaGetLastError();
-}
-
-template <int D, int MODE>
-cudaError_t tile_gather(const float* keys, const float* t1, const int* t2, const float* in, const float* pad,
-                        float* out, float* grad_keys, const ctb_shape* s, cudaStream_t stream) {
-  GatherConfig c;
-  if (!gather_config(s, MODE, &c)) return cudaErrorNotSupported;
-  switch (c.PPT) {
-    case 1: return launch_gather<D, MODE, 1>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
-    case 2: return launch_gather<D, MODE, 2>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
-    case 4: return launch_gather<D, MODE, 4>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
-    default: return launch_gather<D, MODE, 8>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
-  }
 }
 
 }  // namespace ctb
