@@ -126,7 +126,7 @@ splat_fwd_atomic_kernel(PointSource src, const float* __restrict__ feat, const f
   }
 }
 
-// A4: Slice forward (gather).  Sequential float32 sum over corners, one rounding per op.
+// A4: Slice forward (gather).  Sequential float32 accumulation over corners (first product, then FMAs).
 template <int D, bool KEYS>
 __global__ void __launch_bounds__(kGenericBlock)
 slice_fwd_kernel(PointSource src, const float* __restrict__ grid, const float* __restrict__ pad,
@@ -145,8 +145,7 @@ slice_fwd_kernel(PointSource src, const float* __restrict__ grid, const float* _
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const float gv = c.cell[s] >= 0 ? __ldg(gu + (size_t)f * g.C + c.cell[s]) : 0.0f;
-      const float t = CTB_FMUL(gv, c.w[s]);
-      acc = (s == 0) ? t : CTB_FADD(acc, t);
+      acc = (s == 0) ? CTB_FMUL(gv, c.w[s]) : fmaf(gv, c.w[s], acc);
     }
     if (pad) acc = CTB_FMUL(acc, pd);
     ou[(size_t)f * N] = acc;
