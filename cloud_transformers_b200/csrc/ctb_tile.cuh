@@ -67,7 +67,8 @@ inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* ou
   const int rows = W0 - halo;                  // base rows (gather) / destination rows (scatter)
   if (s->N > kTileMaxPoints) return false;
   const long long entries = (long long)s->N << s->dim;
-  const int layout = entries >= C ? TILE_CL : ((stride0 % 4 == 0) ? TILE_PM4 : TILE_PM1);
+  // channel-last only pays when the per-entry work dwarfs the tile move (coarse, dense grids)
+  const int layout = entries >= 8 * C ? TILE_CL : ((stride0 % 4 == 0) ? TILE_PM4 : TILE_PM1);
   const size_t list_bytes = (((size_t)s->N + 7) & ~(size_t)7) * 2 + 16;  // uint16 list + counter
   auto bytes = [&](long long cells, int FG) {
     return (size_t)tile_array_words((int)cells, FG, layout) * 4 * arrays + list_bytes;
@@ -169,10 +170,10 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   const int cs = CL ? (FG | 1) : 1;             // word stride between cells
   const int fs = CL ? 1 : tile_cells;           // word stride between channels
   const bool want_arg = !SUM && arg != nullptr;
-  float* tval = (float*)smem_raw;
-  int* targ = (int*)(tval + tw);                                    // (max with arg only)
-  unsigned short* sel = (unsigned short*)(targ + (want_arg ? tw : 0));
-  int* counter = (int*)(sel + ((N + 7) & ~7));
+  float* tval = (float*)smem_raw;                                   // max: value bits   | sum: low limb
+  int* targ = (int*)(tval + tw);                                    // max: arg (if any) | sum: high limb
+  unsigned short* sel = (unsigned short*)(targ + ((SUM || want_arg) ? tw : 0));
+  int* counter = (int*)(sel + ((N + 7) & ~7));                      // [0] compaction, [1] max|v| bits, [2] non-finite
 
   int item = blockIdx.x;
   const int slab = item % slabs;
@@ -189,8 +190,10 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     int4* a4 = reinterpret_cast<int4*>(targ);
     for (int i = threadIdx.x; i < (tw >> 2); i += kTileThreads) {
       t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (want_arg) a4[i] = make_int4(0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF);
+      if (SUM) a4[i] = make_int4(0, 0, 0, 0);
+      else if (want_arg) a4[i] = make_int4(0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF);
     }
+    if (threadIdx.x == 0) counter[1] = counter[2] = 0;
   }
   const float* ku = keys + (size_t)unit * D * N;
   const float* pu = pad ? pad + (size_t)(unit / H) * N : nullptr;
@@ -198,6 +201,40 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   int cnt = N;
   if (slabs > 1) cnt = compact_slab_points<D, true>(ku, N, g, x0, x1, sel, counter);
   else __syncthreads();
+
+  // sum: pick the fixed-point scale 2^k from M = max |feature * pad| of this item, so that cnt * M * 2^k < 2^62
+  // (|w| <= 1, a point hits a cell at most once).  Any k gives the same exact integer sum, so the result does not
+  // depend on k as long as nothing overflows; non-finite inputs fall back to float atomics.
+  bool fixed_point = false;
+  float scale = 1.0f, inv_scale = 1.0f;
+  if constexpr (SUM) {
+    float m = 0.0f;
+    bool bad = false;
+    for (int i = threadIdx.x; i < cnt; i += kTileThreads) {
+      const int n = slabs > 1 ? (int)sel[i] : i;
+      const float pd = pu ? __ldg(pu + n) : 1.0f;
+      for (int f = 0; f < fg; ++f) {
+        const float v = fabsf(__ldg(fu + (size_t)f * N + n) * pd);
+        bad |= !(v <= 3.0e38f);
+        m = fmaxf(m, v);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(counter + 1, __float_as_int(m));
+      if (bad) counter[2] = 1;
+    }
+    __syncthreads();
+    const float M = __int_as_float(counter[1]);
+    fixed_point = counter[2] == 0;
+    if (fixed_point && M > 0.0f) {
+      int k = 62 - (ilogbf(M) + 1) - (32 - __clz(cnt > 1 ? cnt : 1));
+      k = k > 120 ? 120 : k;
+      scale = ldexpf(1.0f, k);
+      inv_scale = ldexpf(1.0f, -k);
+    }
+  }
 
 #pragma unroll 1
   for (int pass = 0; pass < (want_arg ? 2 : 1); ++pass) {
@@ -220,13 +257,32 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
       const float pd = pu ? __ldg(pu + n) : 1.0f;
       const float* fp = fu + n;
       if constexpr (SUM) {
+        if (fixed_point) {
+          // exact, order-independent accumulation: q = v * 2^k as int64, added as (lo, hi) 32-bit limbs with the
+          // carry taken from the value the lo atomic returns; sum of carries == number of lo wrap-arounds
+          unsigned* lo_t = (unsigned*)tval;
 #pragma unroll 2
-        for (int f = 0; f < fg; ++f) {
-          float ft = __ldg(fp + (size_t)f * N);
-          if (pu) ft = CTB_FMUL(ft, pd);
+          for (int f = 0; f < fg; ++f) {
+            float ft = __ldg(fp + (size_t)f * N);
+            if (pu) ft = CTB_FMUL(ft, pd);
 #pragma unroll
-          for (int s = 0; s < S; ++s)
-            if (w[s] != 0.0f) atomicAdd(tval + a[s] + f * fs, CTB_FMUL(ft, w[s]));
+            for (int s = 0; s < S; ++s) {
+              const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(ft, w[s]), scale));
+              const unsigned lo = (unsigned)q;
+              const unsigned old = atomicAdd(lo_t + a[s] + f * fs, lo);
+              const int hi = (int)(q >> 32) + ((unsigned)(old + lo) < old ? 1 : 0);
+              if (hi != 0) atomicAdd(targ + a[s] + f * fs, hi);
+            }
+          }
+        } else {
+#pragma unroll 2
+          for (int f = 0; f < fg; ++f) {
+            float ft = __ldg(fp + (size_t)f * N);
+            if (pu) ft = CTB_FMUL(ft, pd);
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+              if (w[s] != 0.0f) atomicAdd(tval + a[s] + f * fs, CTB_FMUL(ft, w[s]));
+          }
         }
       } else if (pass == 0) {
 #pragma unroll 4
@@ -256,10 +312,21 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   // store the slab once, coalesced; arg's "no winner" marker becomes -1
   float* zu = z + ((size_t)unit * F + f0) * g.C + cell0;
   int* au = want_arg ? arg + ((size_t)unit * F + f0) * g.C + cell0 : nullptr;
+  auto limbs_to_float = [&](float lo_bits, int hi) {
+    const long long q = ((long long)hi << 32) | (long long)(unsigned)__float_as_int(lo_bits);
+    return __ll2float_rn(q) * inv_scale;
+  };
   if constexpr (LAYOUT == TILE_PM4) {
     for_each_plane_element(fg, ncell >> 2, [&](int f, int r) {
-      __stcs(reinterpret_cast<float4*>(zu + (size_t)f * g.C) + r,
-             reinterpret_cast<const float4*>(tval + (size_t)f * tile_cells)[r]);
+      float4 v4 = reinterpret_cast<const float4*>(tval + (size_t)f * tile_cells)[r];
+      if (SUM && fixed_point) {
+        const int4 h4 = reinterpret_cast<const int4*>(targ + (size_t)f * tile_cells)[r];
+        v4.x = limbs_to_float(v4.x, h4.x);
+        v4.y = limbs_to_float(v4.y, h4.y);
+        v4.z = limbs_to_float(v4.z, h4.z);
+        v4.w = limbs_to_float(v4.w, h4.w);
+      }
+      __stcs(reinterpret_cast<float4*>(zu + (size_t)f * g.C) + r, v4);
       if (want_arg) {
         int4 v = reinterpret_cast<const int4*>(targ + (size_t)f * tile_cells)[r];
         v.x = v.x == 0x7FFFFFFF ? -1 : v.x;
@@ -271,7 +338,9 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     });
   } else {
     for_each_plane_element(fg, ncell, [&](int f, int r) {
-      __stcs(zu + (size_t)f * g.C + r, tval[r * cs + f * fs]);
+      float v1 = tval[r * cs + f * fs];
+      if (SUM && fixed_point) v1 = limbs_to_float(v1, targ[r * cs + f * fs]);
+      __stcs(zu + (size_t)f * g.C + r, v1);
       if (want_arg) {
         const int v = targ[r * cs + f * fs];
         __stcs(au + (size_t)f * g.C + r, v == 0x7FFFFFFF ? -1 : v);
@@ -281,7 +350,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
 }
 
 inline bool tile_scatter_config(const ctb_shape* s, bool sum, bool want_arg, TileConfig* out) {
-  return tile_config(s, (sum || !want_arg) ? 1 : 2, 0, out);
+  return tile_config(s, (sum || want_arg) ? 2 : 1, 0, out);
 }
 
 template <int D, bool SUM, int LAYOUT>
