@@ -40,6 +40,42 @@ constexpr int kTileMaxPoints = 65535;  // compacted point lists are uint16
 
 enum TileLayout { TILE_PM4 = 0, TILE_PM1 = 1, TILE_CL = 2 };
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier: a plane slab is one contiguous byte range both in
+// HBM and in a plane-major tile, so one elected thread moves a whole tile with a handful of instructions and
+// the copy engine overlaps it with whatever the CTA does next (point compaction, position arithmetic).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_and_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct TileConfig {
   int FG;      // channels per tile
   int R;       // base rows (axis 0) per slab
@@ -69,7 +105,7 @@ inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* ou
   const long long entries = (long long)s->N << s->dim;
   // channel-last only pays when the per-entry work dwarfs the tile move (coarse, dense grids)
   const int layout = entries >= 8 * C ? TILE_CL : ((stride0 % 4 == 0) ? TILE_PM4 : TILE_PM1);
-  const size_t list_bytes = (((size_t)s->N + 7) & ~(size_t)7) * 2 + 16;  // uint16 list + counter
+  const size_t list_bytes = (((size_t)s->N + 7) & ~(size_t)7) * 2 + 32;  // uint16 list + counters + mbarrier
   auto bytes = [&](long long cells, int FG) {
     return (size_t)tile_array_words((int)cells, FG, layout) * 4 * arrays + list_bytes;
   };
@@ -191,7 +227,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     for (int i = threadIdx.x; i < (tw >> 2); i += kTileThreads) {
       t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (SUM) a4[i] = make_int4(0, 0, 0, 0);
-      else if (want_arg) a4[i] = make_int4(0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF);
+      else if (want_arg) a4[i] = make_int4(-1, -1, -1, -1);   // "no winner" == max unsigned
     }
     if (threadIdx.x == 0) counter[1] = counter[2] = 0;
   }
@@ -206,6 +242,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   // (|w| <= 1, a point hits a cell at most once).  Any k gives the same exact integer sum, so the result does not
   // depend on k as long as nothing overflows; non-finite inputs fall back to float atomics.
   bool fixed_point = false;
+  int limb_bits = 0;      // > 0: two carry-free limbs of this many bits; 0: 32-bit limbs with carry
   float scale = 1.0f, inv_scale = 1.0f;
   if constexpr (SUM) {
     float m = 0.0f;
@@ -228,8 +265,12 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     __syncthreads();
     const float M = __int_as_float(counter[1]);
     fixed_point = counter[2] == 0;
+    const int cnt_bits = 32 - __clz(cnt > 1 ? cnt - 1 : 1);   // cnt <= 2^cnt_bits
+    if (cnt_bits <= 11) limb_bits = 32 - cnt_bits;            // >= 41 magnitude bits: far below fp32 resolution
     if (fixed_point && M > 0.0f) {
-      int k = 62 - (ilogbf(M) + 1) - (32 - __clz(cnt > 1 ? cnt : 1));
+      // carry-free limbs: |q| < 2^(2*limb_bits-1) per contribution (the count headroom is in the limbs);
+      // carried limbs: the whole sum must stay below 2^62
+      int k = limb_bits > 0 ? (2 * limb_bits - 1) - (ilogbf(M) + 1) : 62 - (ilogbf(M) + 1) - (cnt_bits + 1);
       k = k > 120 ? 120 : k;
       scale = ldexpf(1.0f, k);
       inv_scale = ldexpf(1.0f, -k);
@@ -257,7 +298,23 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
       const float pd = pu ? __ldg(pu + n) : 1.0f;
       const float* fp = fu + n;
       if constexpr (SUM) {
-        if (fixed_point) {
+        if (fixed_point && limb_bits > 0) {
+          // order-independent accumulation without carries: q = v * 2^k (|q| < 2^(2*limb_bits-1)) is split into
+          // an unsigned low limb and a signed high limb; cnt * 2^limb_bits <= 2^32, so neither sum can overflow
+          unsigned* lo_t = (unsigned*)tval;
+          const unsigned lmask = (1u << limb_bits) - 1u;
+#pragma unroll 2
+          for (int f = 0; f < fg; ++f) {
+            float ft = __ldg(fp + (size_t)f * N);
+            if (pu) ft = CTB_FMUL(ft, pd);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(ft, w[s]), scale));
+              atomicAdd(lo_t + a[s] + f * fs, (unsigned)q & lmask);
+              atomicAdd(targ + a[s] + f * fs, (int)(q >> limb_bits));
+            }
+          }
+        } else if (fixed_point) {
           // exact, order-independent accumulation: q = v * 2^k as int64, added as (lo, hi) 32-bit limbs with the
           // carry taken from the value the lo atomic returns; sum of carries == number of lo wrap-arounds
           unsigned* lo_t = (unsigned*)tval;
@@ -298,10 +355,19 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
         for (int f = 0; f < fg; ++f) {
           float ft = __ldg(fp + (size_t)f * N);
           if (pu) ft = CTB_FMUL(ft, pd);
+          // winners are rare: test all corners branch-free first, take the atomic path only if one matched
+          bool hit[S];
+          bool any = false;
 #pragma unroll
           for (int s = 0; s < S; ++s) {
-            const int vi = __float_as_int(CTB_FMUL(ft, w[s]));
-            if (vi > 0 && vi == ((const int*)tval)[a[s] + f * fs]) atomicMin(targ + a[s] + f * fs, s * N + n);
+            const int t = ((const int*)tval)[a[s] + f * fs];
+            hit[s] = (__float_as_int(CTB_FMUL(ft, w[s])) == t) & (t != 0);
+            any |= hit[s];
+          }
+          if (any) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+              if (hit[s]) atomicMin((unsigned*)targ + a[s] + f * fs, (unsigned)(s * N + n));
           }
         }
       }
@@ -309,11 +375,25 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     __syncthreads();
   }
 
-  // store the slab once, coalesced; arg's "no winner" marker becomes -1
+  // store the slab once, coalesced
   float* zu = z + ((size_t)unit * F + f0) * g.C + cell0;
   int* au = want_arg ? arg + ((size_t)unit * F + f0) * g.C + cell0 : nullptr;
+  if constexpr (LAYOUT == TILE_PM4 && !SUM) {
+    // the tile already holds the final bits of z (and arg): hand it to the copy engine, plane by plane
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int f = 0; f < fg; ++f) {
+        bulk_s2g(zu + (size_t)f * g.C, tval + (size_t)f * tile_cells, (uint32_t)ncell * 4u);
+        if (want_arg) bulk_s2g(au + (size_t)f * g.C, targ + (size_t)f * tile_cells, (uint32_t)ncell * 4u);
+      }
+      bulk_commit_and_wait_read();
+    }
+    return;
+  }
   auto limbs_to_float = [&](float lo_bits, int hi) {
-    const long long q = ((long long)hi << 32) | (long long)(unsigned)__float_as_int(lo_bits);
+    const long long lo = (long long)(unsigned)__float_as_int(lo_bits);
+    const long long q = limb_bits > 0 ? ((long long)hi << limb_bits) + lo : (((long long)hi << 32) | lo);
     return __ll2float_rn(q) * inv_scale;
   };
   if constexpr (LAYOUT == TILE_PM4) {
@@ -327,24 +407,16 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
         v4.w = limbs_to_float(v4.w, h4.w);
       }
       __stcs(reinterpret_cast<float4*>(zu + (size_t)f * g.C) + r, v4);
-      if (want_arg) {
-        int4 v = reinterpret_cast<const int4*>(targ + (size_t)f * tile_cells)[r];
-        v.x = v.x == 0x7FFFFFFF ? -1 : v.x;
-        v.y = v.y == 0x7FFFFFFF ? -1 : v.y;
-        v.z = v.z == 0x7FFFFFFF ? -1 : v.z;
-        v.w = v.w == 0x7FFFFFFF ? -1 : v.w;
-        __stcs(reinterpret_cast<int4*>(au + (size_t)f * g.C) + r, v);
-      }
+      if (want_arg)
+        __stcs(reinterpret_cast<int4*>(au + (size_t)f * g.C) + r,
+               reinterpret_cast<const int4*>(targ + (size_t)f * tile_cells)[r]);
     });
   } else {
     for_each_plane_element(fg, ncell, [&](int f, int r) {
       float v1 = tval[r * cs + f * fs];
       if (SUM && fixed_point) v1 = limbs_to_float(v1, targ[r * cs + f * fs]);
       __stcs(zu + (size_t)f * g.C + r, v1);
-      if (want_arg) {
-        const int v = targ[r * cs + f * fs];
-        __stcs(au + (size_t)f * g.C + r, v == 0x7FFFFFFF ? -1 : v);
-      }
+      if (want_arg) __stcs(au + (size_t)f * g.C + r, targ[r * cs + f * fs]);
     });
   }
 }
@@ -414,6 +486,7 @@ tile_gather_kernel(const float* __restrict__ keys, const float* __restrict__ t1,
   int* s2 = (int*)(s1 + tw);                                        // (SPLAT_BWD: arg)
   unsigned short* sel = (unsigned short*)(s2 + (MODE == GATHER_SPLAT_BWD ? tw : 0));
   int* counter = (int*)(sel + ((N + 7) & ~7));
+  uint64_t* bar = (uint64_t*)(counter + 4);     // 16-byte aligned: the list is padded to 8 entries
 
   const int slab = blockIdx.x % slabs;
   const int unit = blockIdx.x / slabs;
@@ -425,29 +498,40 @@ tile_gather_kernel(const float* __restrict__ keys, const float* __restrict__ t1,
   const float* ku = keys + (size_t)unit * D * N;
   const float* pu = pad ? pad + (size_t)(unit / H) * N : nullptr;
 
+  if constexpr (LAYOUT == TILE_PM4) {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+  }
   int cnt = N;
-  if (slabs > 1) cnt = compact_slab_points<D, false>(ku, N, g, x0, x1, sel, counter);
+  if (LAYOUT != TILE_PM4 && slabs > 1) cnt = compact_slab_points<D, false>(ku, N, g, x0, x1, sel, counter);
 
+  uint32_t parity = 0;
   for (int f0 = 0; f0 < F; f0 += FG) {
     const int fg = min(FG, F - f0);
     if (f0 > 0) __syncthreads();                 // previous group's readers are done with the tile
     const float* g1 = t1 + ((size_t)unit * F + f0) * g.C + cell0;
     const int* g2 = MODE == GATHER_SPLAT_BWD ? t2 + ((size_t)unit * F + f0) * g.C + cell0 : nullptr;
     if constexpr (LAYOUT == TILE_PM4) {
-      for_each_plane_element(fg, ncell >> 2, [&](int f, int r) {
-        reinterpret_cast<float4*>(s1 + (size_t)f * tile_cells)[r] =
-            __ldcs(reinterpret_cast<const float4*>(g1 + (size_t)f * g.C) + r);
-        if constexpr (MODE == GATHER_SPLAT_BWD)
-          reinterpret_cast<int4*>(s2 + (size_t)f * tile_cells)[r] =
-              __ldcs(reinterpret_cast<const int4*>(g2 + (size_t)f * g.C) + r);
-      });
+      // one thread hands the whole tile to the copy engine; the CTA compacts its points meanwhile
+      if (threadIdx.x == 0) {
+        const uint32_t plane_bytes = (uint32_t)ncell * 4u;
+        mbar_expect_tx(bar, plane_bytes * fg * (MODE == GATHER_SPLAT_BWD ? 2u : 1u));
+        for (int f = 0; f < fg; ++f) {
+          bulk_g2s(s1 + (size_t)f * tile_cells, g1 + (size_t)f * g.C, plane_bytes, bar);
+          if constexpr (MODE == GATHER_SPLAT_BWD)
+            bulk_g2s(s2 + (size_t)f * tile_cells, g2 + (size_t)f * g.C, plane_bytes, bar);
+        }
+      }
+      if (f0 == 0 && slabs > 1) cnt = compact_slab_points<D, false>(ku, N, g, x0, x1, sel, counter);
+      mbar_wait(bar, parity);
+      parity ^= 1u;
     } else {
       for_each_plane_element(fg, ncell, [&](int f, int r) {
         s1[r * cs + f * fs] = __ldcs(g1 + (size_t)f * g.C + r);
         if constexpr (MODE == GATHER_SPLAT_BWD) s2[r * cs + f * fs] = __ldcs(g2 + (size_t)f * g.C + r);
       });
+      __syncthreads();
     }
-    __syncthreads();
 #pragma unroll 1
     for (int i = threadIdx.x; i < cnt; i += kTileThreads) {
       const int n = slabs > 1 ? (int)sel[i] : i;

@@ -347,11 +347,13 @@ def test_non_default_stream_and_noncontiguous_inputs():
     assert np.array_equal(n(z), ref["z"])
 
 
-def test_tile_sum_is_order_independent_and_correctly_rounded():
-    """TILE-mode scatter-add accumulates exact 64-bit fixed-point integers (two 32-bit shared atomics with carry):
-    the result is the correctly rounded exact sum, so it is bit-identical from run to run AND invariant under
-    any permutation of the points -- stronger than a fixed summation order."""
-    for dim, W, H, F, N, B in [(3, 8, 2, 32, 2048, 2), (2, 64, 2, 16, 2048, 1), (3, 32, 2, 4, 2048, 1)]:
+def test_tile_sum_is_order_independent_and_accurate():
+    """TILE-mode scatter-add accumulates fixed-point integers with native shared-memory atomics (integer addition
+    is associative): the result is bit-identical from run to run AND invariant under any permutation of the
+    points -- stronger than a fixed summation order -- and closer to the exact sum than float accumulation:
+    |err| <= 2^-24 |exact| + N * 2^-41 * max|feature|."""
+    for dim, W, H, F, N, B in [(3, 8, 2, 32, 2048, 2), (2, 64, 2, 16, 2048, 1), (3, 32, 2, 4, 2048, 1),
+                               (2, 16, 2, 8, 5000, 1)]:
         keys, feat, pad = make_inputs(31, B, H, dim, F, N, pad=True)
         geom = CF.Geometry(O._sizes(W, dim), H, dim)
         rng = np.random.default_rng(4)
@@ -363,7 +365,6 @@ def test_tile_sum_is_order_independent_and_correctly_rounded():
             with torch.no_grad():
                 outs.append(n(CF.fused_splat(h, t(f_), t(p_), _lib.REDUCE_SUM)))
         assert np.array_equal(outs[0], outs[1]), "sum must not depend on the order of the points"
-        # reference: exact sum in float64, rounded once
         lc, idx = O.positions_fwd(keys, W, H, dim)
         pre = O._pre_splat(lc, feat, pad, H).astype(np.float64)
         Bq, Hq, Fq, Sq, Nq = pre.shape
@@ -372,5 +373,7 @@ def test_tile_sum_is_order_independent_and_correctly_rounded():
         rows = np.broadcast_to(np.arange(Bq * Hq * Fq)[:, None], (Bq * Hq * Fq, Sq * Nq))
         index = np.broadcast_to(idx.reshape(Bq, Hq, 1, Sq * Nq), (Bq, Hq, Fq, Sq * Nq)).reshape(Bq * Hq * Fq, Sq * Nq)
         np.add.at(ex, (rows, index), pre.reshape(Bq * Hq * Fq, Sq * Nq))
-        ref = ex.astype(np.float32).reshape(outs[0].shape)
-        assert np.array_equal(outs[0], ref), "fixed-point sum must equal the correctly rounded exact sum"
+        ex = ex.reshape(outs[0].shape)
+        err = np.abs(outs[0].astype(np.float64) - ex)
+        bound = 2.0 ** -24 * np.abs(ex) + N * 2.0 ** -41 * float(np.abs(feat).max())
+        assert (err <= bound).all(), float((err - bound).max())
