@@ -6,6 +6,7 @@
 #include "ctb_generic.cuh"
 #include "ctb_sorted.cuh"
 #include "ctb_tile.cuh"
+#include "ctb_tile_cl.cuh"
 
 namespace {
 
@@ -157,6 +158,18 @@ int slice_bwd_atomic_impl(ctb::PointSource src, const float* grid, const float* 
   return CTB_OK;
 }
 
+// TILE-mode scatter: channel-lane kernel for coarse dense grids, point-lane kernel otherwise
+template <int D>
+cudaError_t tile_scatter_any(const float* keys, const float* feat, const float* pad, float* z, int* arg,
+                             const ctb_shape* s, bool sum, cudaStream_t stream) {
+  static const bool no_cl = getenv("CTB_NO_CHANNEL_LANE") != nullptr;
+  cudaError_t e = cudaSuccess;
+  // measured (profiles/r01_*): lanes = channels wins for the contended float-sum atomics (c3d 0.52 -> 0.32 ms) but
+  // not for max, whose second pass is broadcast-friendly shared loads
+  if (!no_cl && sum && ctb::cl_scatter_try<D>(keys, feat, pad, z, arg, s, sum, stream, &e)) return e;
+  return ctb::tile_scatter<D>(keys, feat, pad, z, arg, s, sum, stream);
+}
+
 #define CTB_DISPATCH_DIM(shape, call2, call3) ((shape)->dim == 2 ? (call2) : (call3))
 
 }  // namespace
@@ -302,8 +315,8 @@ int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pa
   if (mode == CTB_MODE_TILE) {
     const bool sum = reduce == CTB_REDUCE_SUM;
     return cuda_status(shape->dim == 2
-                           ? ctb::tile_scatter<2>(keys, features, pad, z, sum ? nullptr : arg, shape, sum, (cudaStream_t)stream)
-                           : ctb::tile_scatter<3>(keys, features, pad, z, sum ? nullptr : arg, shape, sum, (cudaStream_t)stream));
+                           ? tile_scatter_any<2>(keys, features, pad, z, sum ? nullptr : arg, shape, sum, (cudaStream_t)stream)
+                           : tile_scatter_any<3>(keys, features, pad, z, sum ? nullptr : arg, shape, sum, (cudaStream_t)stream));
   }
   if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;
   ctb::PointSource src{keys, nullptr, nullptr};
@@ -369,8 +382,8 @@ int ctb_slice_bwd_keys(const float* keys, const float* grid, const float* pad, c
                            : ctb::sorted_scatter<3>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream));
     } else {
       st = cuda_status(shape->dim == 2
-                           ? ctb::tile_scatter<2>(keys, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream)
-                           : ctb::tile_scatter<3>(keys, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream));
+                           ? tile_scatter_any<2>(keys, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream)
+                           : tile_scatter_any<3>(keys, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream));
     }
     if (st) return st;
     // ... and grad_keys: tile gather against the convolved grid.

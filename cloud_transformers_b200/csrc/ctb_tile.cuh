@@ -28,6 +28,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/ctb200.h"
 #include "ctb_positions.cuh"
 
@@ -117,12 +118,16 @@ inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* ou
     out->words = tile_array_words((slabs == 1 ? W0 : R + halo) * stride0, FG, layout);
     out->smem = (size_t)out->words * 4 * arrays + list_bytes;
   };
+  // tuning knobs for experiments (not part of the ABI): CTB_TILE_BUDGET_KB, CTB_TILE_MIN_GROUP
+  static const int env_budget = getenv("CTB_TILE_BUDGET_KB") ? atoi(getenv("CTB_TILE_BUDGET_KB")) : 0;
+  static const int env_min_group = getenv("CTB_TILE_MIN_GROUP") ? atoi(getenv("CTB_TILE_MIN_GROUP")) : 3;
   for (int pass = 0; pass < 2; ++pass) {
-    const size_t budget = pass == 0 ? kTileSmemTwoCtas : kTileSmemMax;
+    size_t budget = pass == 0 ? kTileSmemTwoCtas : kTileSmemMax;
+    if (pass == 0 && env_budget > 0) budget = (size_t)env_budget * 1024;
     // (1) whole grid, channel groups
     int FG = s->F;
     while (FG > 1 && bytes(C, FG) > budget) --FG;
-    if (bytes(C, FG) <= budget && (FG >= 3 || FG == s->F)) {
+    if (bytes(C, FG) <= budget && (FG >= env_min_group || FG == s->F)) {
       const int groups = (s->F + FG - 1) / FG;
       fill((s->F + groups - 1) / groups, rows, 1);
       return true;
