@@ -7,6 +7,7 @@
 #include "ctb_sorted.cuh"
 #include "ctb_tile.cuh"
 #include "ctb_tile_cl.cuh"
+#include "ctb_project.cuh"
 
 namespace {
 
@@ -398,6 +399,44 @@ int ctb_slice_bwd_keys(const float* keys, const float* grid, const float* pad, c
   return CTB_DISPATCH_DIM(
       shape, (slice_bwd_atomic_impl<2, true>(src, grid, pad, grad_out, grad_grid, grad_keys, shape, stream)),
       (slice_bwd_atomic_impl<3, true>(src, grid, pad, grad_out, grad_grid, grad_keys, shape, stream)));
+}
+
+int ctb_project_fwd(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
+                    const float* scales, float* keys, const ctb_shape* shape, void* stream) {
+  int st = check_shape(shape, false);
+  if (st) return st;
+  if (!pcd || !shift || !rot || !keys) return CTB_ERR_INVALID_ARGUMENT;
+  const int chunks = (shape->N + ctb::kProjBlock - 1) / ctb::kProjBlock;
+  const unsigned blocks = (unsigned)((long long)shape->B * shape->H * chunks);
+  if (shape->dim == 2)
+    ctb::project_fwd_kernel<2><<<blocks, ctb::kProjBlock, 0, (cudaStream_t)stream>>>(pcd, keys_res, res_scale, shift, rot,
+                                                                                     scales, keys, shape->H, shape->N, chunks);
+  else
+    ctb::project_fwd_kernel<3><<<blocks, ctb::kProjBlock, 0, (cudaStream_t)stream>>>(pcd, keys_res, res_scale, shift, rot,
+                                                                                     scales, keys, shape->H, shape->N, chunks);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+int ctb_project_bwd(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
+                    const float* scales, const float* keys, const float* grad_keys, float* grad_pcd,
+                    float* grad_keys_res, float* param_acc, const ctb_shape* shape, void* stream) {
+  int st = check_shape(shape, false);
+  if (st) return st;
+  if (!pcd || !shift || !rot || !keys || !grad_keys || !grad_pcd || !param_acc) return CTB_ERR_INVALID_ARGUMENT;
+  if (keys_res && !grad_keys_res) return CTB_ERR_INVALID_ARGUMENT;
+  const int chunks = (shape->N + ctb::kProjBlock - 1) / ctb::kProjBlock;
+  const unsigned blocks = (unsigned)((long long)shape->B * chunks);
+  if (shape->dim == 2)
+    ctb::project_bwd_kernel<2><<<blocks, ctb::kProjBlock, 0, (cudaStream_t)stream>>>(
+        pcd, keys_res, res_scale, shift, rot, scales, keys, grad_keys, grad_pcd, grad_keys_res, param_acc, shape->H,
+        shape->N, chunks);
+  else
+    ctb::project_bwd_kernel<3><<<blocks, ctb::kProjBlock, 0, (cudaStream_t)stream>>>(
+        pcd, keys_res, res_scale, shift, rot, scales, keys, grad_keys, grad_pcd, grad_keys_res, param_acc, shape->H,
+        shape->N, chunks);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
 }
 
 int ctb_count_occupied(const float* z, uint64_t n_elements, unsigned long long* count, void* stream) {

@@ -330,3 +330,53 @@ def count_occupied(z):
     with torch.cuda.device(z_c.device):
         _call("ctb_count_occupied", _ptr(z_c), ctypes.c_uint64(z_c.numel()), _ptr(cnt), _stream(z_c))
     return cnt[0]
+
+
+# ---------------------------------------------------------------------------------------------------
+# A8: fused per-head projection + tanh (VolTransformer / PlaneTransformer + torch.tanh of the MHCT blocks)
+class _ProjectFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pcd, keys_res, res_scale, shift, rot, scales, heads, dim):
+        _require_cuda(pcd, keys_res, shift, rot, scales)
+        pcd_c, res_c = _f32c(pcd), _f32c(keys_res)
+        shift_c, rot_c, scales_c = _f32c(shift), _f32c(rot), _f32c(scales)
+        B, _, N = pcd_c.shape
+        rs = 1.0 if res_scale is None else float(res_scale)
+        keys = torch.empty((B, heads * dim, N), dtype=torch.float32, device=pcd_c.device)
+        sh = _lib.make_shape(B, heads, 1, N, dim, (2,) * dim)
+        with torch.cuda.device(pcd_c.device):
+            _call("ctb_project_fwd", _ptr(pcd_c), _ptr(res_c), ctypes.c_float(rs), _ptr(shift_c), _ptr(rot_c),
+                  _ptr(scales_c), _ptr(keys), ctypes.byref(sh), _stream(pcd_c))
+        ctx.save_for_backward(pcd_c, res_c, shift_c, rot_c, scales_c, keys)
+        ctx.rs, ctx.heads, ctx.dim = rs, heads, dim
+        ctx.res_scale_is_tensor = isinstance(res_scale, torch.Tensor)
+        return keys
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_keys):
+        pcd_c, res_c, shift_c, rot_c, scales_c, keys = ctx.saved_tensors
+        B, _, N = pcd_c.shape
+        heads, dim = ctx.heads, ctx.dim
+        g = _f32c(g_keys)
+        g_pcd = torch.empty_like(pcd_c)
+        g_res = torch.empty_like(res_c) if res_c is not None else None
+        acc = torch.zeros((heads, 16), dtype=torch.float32, device=pcd_c.device)
+        sh = _lib.make_shape(B, heads, 1, N, dim, (2,) * dim)
+        with torch.cuda.device(pcd_c.device):
+            _call("ctb_project_bwd", _ptr(pcd_c), _ptr(res_c), ctypes.c_float(ctx.rs), _ptr(shift_c), _ptr(rot_c),
+                  _ptr(scales_c), _ptr(keys), _ptr(g), _ptr(g_pcd), _ptr(g_res), _ptr(acc), ctypes.byref(sh),
+                  _stream(pcd_c))
+        g_shift = acc[:, 0:3].contiguous()
+        g_rot = acc[:, 3:12].reshape(heads, 3, 3)
+        g_scales = acc[:, 12:12 + dim].contiguous() if scales_c is not None else None
+        g_rs = acc[:, 15].sum() if ctx.res_scale_is_tensor else None
+        return g_pcd, g_res, g_rs, g_shift, g_rot, g_scales, None, None
+
+
+def project_keys(orig_pcd, keys_res, shift, rot, scales=None, res_scale=None, *, heads, dim):
+    """tanh(((orig_pcd + res_scale * keys_res + shift) . rot)[:dim] * scales) -> keys [B, heads*dim, N].
+
+    orig_pcd [B,3,N]; keys_res [B, heads*3, N] or [B,heads,3,N] or None; shift [heads,3]; rot [heads,3,3];
+    scales [heads,dim] or None; res_scale None / python float / 0-dim tensor (MultiHeadAdaIn's `scale`)."""
+    return _ProjectFn.apply(orig_pcd, keys_res, res_scale, shift, rot, scales, heads, dim)

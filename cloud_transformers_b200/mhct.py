@@ -1,0 +1,139 @@
+"""Host-side mirror of the reference's MHCT blocks (layers/multihead_ct.py:9-198, layers/multihead_ct_pool.py:9-86)
+wired to the fused B200 kernels -- the callers either side of the hot path.
+
+Same constructor arguments, sub-module / parameter names (so reference checkpoints load with strict=True) and
+return contract `(result, stats)` as the reference; the forward differs only in HOW the path is computed:
+  * keys: one fused kernel for shift + rotation + scales + tanh (ctb_project_fwd) instead of add / einsum / tanh
+  * positions are never materialised: Splat / Slice take the keys directly (fused_splat / fused_slice)
+  * the occupancy statistic is one counting pass without host sync (ctb_count_occupied)
+The dense contractions (1x1 Conv1d, BatchNorm, grouped 3x3(x3) conv) stay in PyTorch / cuDNN, as the north star says.
+"""
+import torch
+from torch import nn
+
+from . import functional as CF
+from .cloud_transform import DifferentiablePositions, Slice, Splat
+from .so3 import so3_exponential_map
+
+
+class _Transformer(nn.Module):
+    """Parameters of VolTransformer / PlaneTransformer (layers/utils.py:9-61): log_R, shift, optional scales."""
+
+    def __init__(self, heads, dim, scales=False):
+        super().__init__()
+        self.heads, self.dim = heads, dim
+        self.log_R = nn.Parameter(torch.randn(heads, 3, dtype=torch.float32))
+        self.shift = nn.Parameter(torch.zeros(heads, 3, dtype=torch.float32))
+        self.do_scales = scales
+        if scales:
+            self.scales = nn.Parameter(torch.ones(heads, dim, dtype=torch.float32))
+
+    def keys(self, orig_pcd, keys_res, res_scale=None):
+        rot = so3_exponential_map(self.log_R)
+        return CF.project_keys(orig_pcd, keys_res, self.shift, rot, self.scales if self.do_scales else None,
+                               res_scale, heads=self.heads, dim=self.dim)
+
+
+class MultiHead(nn.Module):
+    def __init__(self, model_dim, in_feature_dim, out_model_dim, tensor_size, tensor_dim, heads, scales=False):
+        super().__init__()
+        assert tensor_dim in (2, 3)
+        self.in_feature_dim, self.out_model_dim = in_feature_dim, out_model_dim
+        self.model_dim, self.tensor_size, self.tensor_dim, self.heads = model_dim, tensor_size, tensor_dim, heads
+        self.keys_values_pred = nn.Sequential(nn.Conv1d(model_dim, heads * (in_feature_dim + 3), kernel_size=1, bias=False))
+        self.values_bn = nn.BatchNorm1d(heads * in_feature_dim)
+        self.key_bn = nn.BatchNorm1d(heads * 3)
+        # kept for their `tensor_mod` buffers (checkpoint compatibility) and for callers that want lc / idx
+        self.diff_poss = DifferentiablePositions(tensor_size=tensor_size, dim=tensor_dim, heads=heads)
+        self.splat = Splat(tensor_size=tensor_size, dim=tensor_dim, heads=heads)
+        self.slice = Slice(tensor_size=tensor_size, dim=tensor_dim, heads=heads)
+        conv = nn.Conv3d if tensor_dim == 3 else nn.Conv2d
+        self.conv = nn.Sequential(conv(heads * in_feature_dim, heads * in_feature_dim, kernel_size=3, stride=1, padding=1,
+                                       groups=heads, bias=True))
+        self.after = nn.Sequential(nn.BatchNorm1d(heads * in_feature_dim), nn.ReLU(inplace=True))
+        self.transform = _Transformer(heads, tensor_dim, scales)
+        sizes = [tensor_size] * tensor_dim if isinstance(tensor_size, int) else list(tensor_size)
+        self._geom = CF.Geometry(sizes, heads, tensor_dim)
+        torch.nn.init.zeros_(self.key_bn.weight)       # multihead_ct.py:79-80
+
+    def forward(self, input, orig_pcd, return_lattice=False):
+        if isinstance(orig_pcd, tuple):                # (points, padding mask), multihead_ct.py:84-87
+            orig_pcd, pts_padd = orig_pcd
+        else:
+            pts_padd = None
+        key_values = self.keys_values_pred(input)
+        keys_res = self.key_bn(key_values[:, :self.heads * 3])
+        values = self.values_bn(key_values[:, self.heads * 3:])
+        lattice = self.transform.keys(orig_pcd, keys_res)                   # A8, fused
+        handle = CF.PositionsHandle(lattice, self._geom)
+        z = CF.fused_splat(handle, values, pts_padd)                        # A1 + A2 + A3
+        with torch.no_grad():
+            occ = CF.count_occupied(z).float() / (input.size(0) * self.in_feature_dim * self.heads)   # A9
+        result = self.after(CF.fused_slice(handle, self.conv(z), pts_padd))  # A4
+        with torch.no_grad():
+            # the reference logs mean / var of the pre-tanh keys; they are recovered from the lattice (equal up to
+            # tanh saturation) so that the pre-tanh tensor never has to be materialised
+            pre = torch.atanh(lattice.detach().clamp(-1 + 1e-7, 1 - 1e-7))
+            stats = (occ, pre.mean(), pre.var(), None)
+        if return_lattice:
+            result = result, lattice
+        return result, stats
+
+
+class MultiHeadPool(nn.Module):
+    def __init__(self, model_dim, in_feature_dim, tensor_size, tensor_dim, heads, scales=False):
+        super().__init__()
+        assert tensor_dim in (2, 3)
+        self.in_feature_dim, self.model_dim = in_feature_dim, model_dim
+        self.tensor_size, self.tensor_dim, self.heads = tensor_size, tensor_dim, heads
+        self.keys_values_pred = nn.Sequential(nn.Conv1d(model_dim, heads * (in_feature_dim + 3), kernel_size=1, bias=False))
+        self.values_bn = nn.BatchNorm1d(heads * in_feature_dim)
+        self.key_bn = nn.BatchNorm1d(heads * 3)
+        self.diff_poss = DifferentiablePositions(tensor_size=tensor_size, dim=tensor_dim, heads=heads)
+        self.splat = Splat(tensor_size=tensor_size, dim=tensor_dim, heads=heads)
+        self.transform = _Transformer(heads, tensor_dim, scales)
+        sizes = [tensor_size] * tensor_dim if isinstance(tensor_size, int) else list(tensor_size)
+        self._geom = CF.Geometry(sizes, heads, tensor_dim)
+        torch.nn.init.zeros_(self.key_bn.weight)
+
+    def forward(self, input, orig_pcd, return_lattice=False):
+        key_values = self.keys_values_pred(input)
+        keys_res = self.key_bn(key_values[:, :self.heads * 3])
+        values = self.values_bn(key_values[:, self.heads * 3:])
+        lattice = self.transform.keys(orig_pcd, keys_res)
+        z = CF.fused_splat(CF.PositionsHandle(lattice, self._geom), values)
+        with torch.no_grad():
+            occ = CF.count_occupied(z).float() / (input.size(0) * self.in_feature_dim * self.heads)
+            pre = torch.atanh(lattice.detach().clamp(-1 + 1e-7, 1 - 1e-7))
+            stats = (occ, pre.mean(), pre.var(), None)
+        result = (z, lattice) if return_lattice else z
+        return result, stats
+
+
+class MultiHeadUnion(nn.Module):
+    def __init__(self, model_dim, features_dims, tensor_sizes, tensor_dims, heads, model_dim_out=None, scales=False):
+        super().__init__()
+        assert len(features_dims) == len(tensor_sizes) == len(tensor_dims) == len(heads)
+        self.model_dim = model_dim
+        self.model_dim_out = model_dim if model_dim_out is None else model_dim_out
+        self.prenorm = nn.Sequential()
+        self.after = nn.Sequential(
+            nn.Conv1d(sum(h * f for h, f in zip(heads, features_dims)), self.model_dim_out, kernel_size=1, bias=False),
+            nn.BatchNorm1d(self.model_dim_out), nn.ReLU(inplace=True))
+        self.shortcut = nn.Sequential()
+        if self.model_dim != self.model_dim_out:
+            self.shortcut.add_module('shortcut_conv', nn.Conv1d(self.model_dim, self.model_dim_out, kernel_size=1, bias=False))
+            self.shortcut.add_module('shortcut_bn', nn.BatchNorm1d(self.model_dim_out))
+        self.attentions = nn.ModuleList([
+            MultiHead(model_dim=model_dim, in_feature_dim=f, out_model_dim=self.model_dim_out, tensor_size=t, tensor_dim=d,
+                      heads=h, scales=scales) for f, t, d, h in zip(features_dims, tensor_sizes, tensor_dims, heads)])
+
+    def forward(self, x, orig_pcd):
+        x = self.prenorm(x)
+        residual = self.shortcut(x)
+        results, stats = [], []
+        for attention in self.attentions:
+            r, s = attention(x, orig_pcd)
+            results.append(r)
+            stats.append(s)
+        return residual + self.after(torch.cat(results, dim=1)), stats

@@ -134,6 +134,21 @@ int ctb_slice_bwd_keys(const float* keys, const float* grid, const float* pad, c
                        float* grad_grid, float* grad_keys, const ctb_shape* shape, int mode,
                        const void* plan, void* stream);
 
+/* ---- A8: per-head projection + tanh in front of DifferentiablePositions ------------------------------ */
+/* keys[b, h*dim + j, n] = tanh( ((pcd[b,:,n] + res_scale*keys_res[b,h,:,n] + shift[h]) . rot[h])_j * scales[h][j] )
+ * Replaces VolTransformer / PlaneTransformer.forward + torch.tanh (layers/utils.py:25-34, :53-61;
+ * layers/multihead_ct.py:93-97; multihead_ct_adain.py:112-115 where res_scale is the learnable `scale`).
+ *   pcd f32 [B,3,N], keys_res f32 [B,H,3,N] or NULL, shift f32 [H,3], rot f32 [H,3,3] (= so3_exponential_map(log_R),
+ *   row-vector convention q_j = sum_c p_c rot[h][c][j]), scales f32 [H,dim] or NULL, keys f32 [B,H*dim,N]. */
+int ctb_project_fwd(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
+                    const float* scales, float* keys, const ctb_shape* shape, void* stream);
+/* Backward of ctb_project_fwd.  grad_pcd f32 [B,3,N] (summed over heads), grad_keys_res f32 [B,H,3,N] or NULL,
+ * param_acc f32 [H,16] ACCUMULATED into (caller zeroes): cols 0-2 d shift, 3-11 d rot (row major c,j; only j < dim
+ * are written), 12-14 d scales, 15 d res_scale (per head; sum over heads for the scalar). */
+int ctb_project_bwd(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
+                    const float* scales, const float* keys, const float* grad_keys, float* grad_pcd,
+                    float* grad_keys_res, float* param_acc, const ctb_shape* shape, void* stream);
+
 /* A9  occupancy statistic of MultiHead blocks (layers/multihead_ct.py:104-105): count of |z| > 1e-9
  * accumulated into *count (u64, device memory, caller zeroes it). */
 int ctb_count_occupied(const float* z, uint64_t n_elements, unsigned long long* count, void* stream);

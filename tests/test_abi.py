@@ -105,3 +105,20 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_mhct_mirror_state_dict_matches_reference():
+    """The MHCT block mirrors keep the reference's parameter / buffer names so released checkpoints load strictly."""
+    from oracle import reference_loader as RL
+    if not RL.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ct, ut, mh = RL.load_reference_layers()
+    from cloud_transformers_b200 import mhct
+    for kw in (dict(model_dim=32, in_feature_dim=4, out_model_dim=32, tensor_size=16, tensor_dim=2, heads=4),
+               dict(model_dim=32, in_feature_dim=8, out_model_dim=32, tensor_size=8, tensor_dim=3, heads=2, scales=True)):
+        ref, ours = mh.MultiHead(**kw), mhct.MultiHead(**kw)
+        assert sorted(ref.state_dict().keys()) == sorted(ours.state_dict().keys())
+        ours.load_state_dict(ref.state_dict(), strict=True)
+    ref = mh.MultiHeadUnion(model_dim=32, features_dims=[4, 4], tensor_sizes=[16, 8], tensor_dims=[2, 3], heads=[4, 4])
+    ours = mhct.MultiHeadUnion(model_dim=32, features_dims=[4, 4], tensor_sizes=[16, 8], tensor_dims=[2, 3], heads=[4, 4])
+    ours.load_state_dict(ref.state_dict(), strict=True)

@@ -377,3 +377,88 @@ def test_tile_sum_is_order_independent_and_accurate():
         err = np.abs(outs[0].astype(np.float64) - ex)
         bound = 2.0 ** -24 * np.abs(ex) + N * 2.0 ** -41 * float(np.abs(feat).max())
         assert (err <= bound).all(), float((err - bound).max())
+
+
+# --- A8: fused projection + tanh, and the MHCT block mirror ------------------------------------------
+def _torch_keys(pcd, keys_res, shift, log_R, scales, res_scale, H, dim):
+    """layers/utils.py:25-34 / :53-61 + multihead_ct.py:93-97 in plain torch."""
+    from cloud_transformers_b200.so3 import so3_exponential_map
+    B, _, N = pcd.shape
+    p = pcd[:, None] + (res_scale if res_scale is not None else 1.0) * keys_res.reshape(B, H, 3, N)
+    p = p + shift[None, :, :, None]
+    q = torch.einsum('bhcp,hcn->bhnp', p, so3_exponential_map(log_R))[:, :, :dim]
+    if scales is not None:
+        q = q * scales[None, :, :, None]
+    return torch.tanh(q.reshape(B, H * dim, N))
+
+
+@pytest.mark.parametrize("dim,with_scales,with_rs", [(2, False, False), (3, True, False), (3, False, True), (2, True, True)])
+def test_fused_projection_matches_torch(dim, with_scales, with_rs):
+    from cloud_transformers_b200.so3 import so3_exponential_map
+    B, H, N = 3, 5, 777
+    g = torch.Generator(device=DEV).manual_seed(dim * 10 + with_scales)
+    pcd = (torch.rand(B, 3, N, device=DEV, generator=g) * 2 - 1).requires_grad_(True)
+    res = (0.3 * torch.randn(B, H * 3, N, device=DEV, generator=g)).requires_grad_(True)
+    shift = (0.1 * torch.randn(H, 3, device=DEV, generator=g)).requires_grad_(True)
+    log_R = torch.randn(H, 3, device=DEV, generator=g).requires_grad_(True)
+    scales = (1 + 0.2 * torch.randn(H, dim, device=DEV, generator=g)).requires_grad_(True) if with_scales else None
+    rs = torch.tensor(0.7, device=DEV, requires_grad=True) if with_rs else None
+    gk = torch.randn(B, H * dim, N, device=DEV, generator=g)
+    ref = _torch_keys(pcd, res, shift, log_R, scales, rs, H, dim)
+    inputs = [t_ for t_ in (pcd, res, shift, log_R, scales, rs) if t_ is not None]
+    g_ref = torch.autograd.grad((ref * gk).sum(), inputs)
+    out = CF.project_keys(pcd, res, shift, so3_exponential_map(log_R), scales, rs, heads=H, dim=dim)
+    g_out = torch.autograd.grad((out * gk).sum(), inputs)
+    assert_close(n(out), n(ref), "keys", rtol=1e-5, atol_scale=2e-6)
+    for a, b_, name in zip(g_out, g_ref, ("pcd", "res", "shift", "log_R", "scales", "res_scale")):
+        assert_close(n(a), n(b_), "grad " + name, rtol=1e-4, atol_scale=1e-4)
+
+
+@pytest.mark.parametrize("dim,W,F", [(2, 16, 8), (3, 8, 4)])
+def test_mhct_block_mirror_matches_unfused_composition(dim, W, F):
+    """MultiHead mirror (fused prologue + fused Splat / Slice) against the same block assembled from torch ops and the
+    reference-API modules.  tanhf may differ from torch.tanh in the last ulp, which can move a point that sits on a
+    cell boundary: the comparison allows a tiny fraction of outliers."""
+    from cloud_transformers_b200 import mhct
+    torch.manual_seed(0)
+    B, H, N, M = 2, 4, 512, 32
+    blk = mhct.MultiHead(model_dim=M, in_feature_dim=F, out_model_dim=M, tensor_size=W, tensor_dim=dim, heads=H,
+                         scales=True).to(DEV)
+    with torch.no_grad():
+        blk.key_bn.weight.normal_(0, 0.3)      # zero-init would switch the learned offsets off
+        blk.transform.scales.normal_(1, 0.1)
+    x = torch.randn(B, M, N, device=DEV, requires_grad=True)
+    pcd = (torch.rand(B, 3, N, device=DEV) * 2 - 1).requires_grad_(True)
+    out, stats = blk(x, pcd)
+    gout = torch.randn_like(out)
+    params = [p for p in blk.parameters() if p.requires_grad]
+    g_fused = torch.autograd.grad((out * gout).sum(), [x, pcd] + params, allow_unused=True)
+
+    def unfused():
+        kv = blk.keys_values_pred(x)
+        keys_res = blk.key_bn(kv[:, :H * 3])
+        values = blk.values_bn(kv[:, H * 3:])
+        lattice = _torch_keys(pcd, keys_res, blk.transform.shift, blk.transform.log_R, blk.transform.scales, None, H, dim)
+        ctb.config.fused = False
+        lc, idx = blk.diff_poss(lattice)
+        z = blk.splat(lc, idx, values)
+        return blk.after(blk.slice(lc, idx, blk.conv(z)))
+
+    ref = unfused()
+    g_ref = torch.autograd.grad((ref * gout).sum(), [x, pcd] + params, allow_unused=True)
+    ctb.config.fused = True
+    bad = (out - ref).abs() > 1e-4 * ref.abs().max() + 1e-4 * ref.abs()
+    assert float(bad.float().mean()) < 2e-3, float(bad.float().mean())
+    names = ["x", "pcd"] + [k for k, p in blk.named_parameters() if p.requires_grad]
+    rels = {}
+    for name, a, b_ in zip(names, g_fused, g_ref):
+        if a is None or b_ is None:
+            assert a is None and b_ is None, name
+            continue
+        rels[name] = (float((a - b_).norm()), float(b_.norm()))
+    top = max(v[1] for v in rels.values())
+    # gradients that are zero in exact arithmetic (e.g. a bias in front of a BatchNorm) are pure rounding noise:
+    # judge every tensor against its own norm plus a floor tied to the largest gradient
+    bad = {k: v for k, v in rels.items() if v[0] > 2e-2 * v[1] + 1e-5 * top}
+    assert not bad, bad
+    assert float(stats[0]) > 0
