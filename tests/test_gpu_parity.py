@@ -462,3 +462,50 @@ def test_mhct_block_mirror_matches_unfused_composition(dim, W, F):
     bad = {k: v for k, v in rels.items() if v[0] > 2e-2 * v[1] + 1e-5 * top}
     assert not bad, bad
     assert float(stats[0]) > 0
+
+
+# --- other BASELINE configs and the sweep extremes ------------------------------
+BIG = [
+    # dim, W, H, F, N, B
+    (3, 32, 16, 4, 4096, 2),      # S3DIS 1x1 block, 3D 32^3
+    (2, 128, 16, 4, 16384, 1),    # inpainting decoder, 2D 128^2
+    (3, 32, 16, 4, 16384, 1),     # inpainting decoder, 3D 32^3
+    (2, 256, 4, 4, 65536, 1),     # sweep: 2D 256^2, N = 64K  (tile kernels at their point-count limit)
+    (3, 64, 4, 4, 32768, 1),      # sweep: 3D 64^3 (one channel plane = 1 MB > shared memory => row slabs)
+    (2, 32, 64, 32, 1024, 1),     # sweep: 64 heads, F = 32
+    (2, 256, 2, 4, 262144, 1),    # sweep max: N = 256K (beyond the tile kernels => L2-atomic kernels)
+]
+
+
+@pytest.mark.parametrize("shape", BIG, ids=lambda s: "d%d_w%d_h%d_f%d_n%d_b%d" % s)
+def test_large_shapes_all_algorithms_agree(shape):
+    dim, W, H, F, N, B = shape
+    g = torch.Generator(device=DEV).manual_seed(7)
+    keys = torch.tanh(torch.randn(B, H * dim, N, device=DEV, generator=g))
+    feat = torch.randn(B, H * F, N, device=DEV, generator=g)
+    res = {}
+    for mode in ("atomic", "auto"):
+        ctb.config.mode = mode
+        dp = ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim)
+        sp = ctb.Splat(tensor_size=W, heads=H, dim=dim)
+        sl = ctb.Slice(tensor_size=W, heads=H, dim=dim)
+        k = keys.clone().requires_grad_(True)
+        f = feat.clone().requires_grad_(True)
+        lc, idx = dp(k)
+        z = sp(lc, idx, f)
+        conv = torch.sin(z * 3 + 0.1)
+        out = sl(lc, idx, conv)
+        gk, gf = torch.autograd.grad(out.square().sum(), [k, f])
+        res[mode] = (z.detach(), out.detach(), gk, gf)
+    za, oa, gka, gfa = res["atomic"]
+    zt, ot, gkt, gft = res["auto"]
+    assert torch.equal(za, zt), "Splat-max grid must agree bit for bit across algorithms"
+    assert torch.allclose(oa, ot, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(gfa, gft, rtol=1e-4, atol=1e-4 * float(gfa.abs().max()))
+    assert torch.allclose(gka, gkt, rtol=1e-4, atol=1e-4 * float(gka.abs().max()))
+    # one unit against the oracle
+    kb, fb = n(keys[:1, :dim]), n(feat[:1, :F])
+    lc_o, idx_o = O.positions_fwd(kb, W, 1, dim)
+    z_o = O.splat_fwd(lc_o, idx_o, fb, W, 1, dim)
+    assert np.array_equal(n(zt[:1, :F]), z_o)
+    assert_close(n(ot[:1, :F]), O.slice_fwd(lc_o, idx_o, np.sin(z_o * 3 + 0.1).astype(np.float32), 1), "slice")
