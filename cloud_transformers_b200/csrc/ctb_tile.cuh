@@ -39,7 +39,7 @@ constexpr int kTileSmemTwoCtas = 110 * 1024;
 constexpr int kTileSmemMax = 220 * 1024;
 constexpr int kTileMaxPoints = 65535;  // compacted point lists are uint16
 
-enum TileLayout { TILE_PM4 = 0, TILE_PM1 = 1, TILE_CL = 2 };
+enum TileLayout { TILE_PM4 = 0, TILE_PM1 = 1, TILE_CL = 2, TILE_CLQ = 3 };
 
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier: a plane slab is one contiguous byte range both in
 // HBM and in a plane-major tile, so one elected thread moves a whole tile with a handful of instructions and
@@ -86,8 +86,13 @@ struct TileConfig {
   size_t smem;
 };
 
+// channel-last pitch in words: CL odd (conflict-free scalar plane moves); CLQ = FG + 4, a multiple of 4 that is not a
+// power of two, so that the 4-channel "quads" of a cell are 16-byte aligned
+__host__ __device__ inline int cl_pitch(int FG, int layout) { return layout == TILE_CLQ ? FG + 4 : (FG | 1); }
+
 inline int tile_array_words(int cells, int FG, int layout) {
-  const long long w = layout == TILE_CL ? (long long)cells * (FG | 1) : (long long)cells * FG;
+  const long long w = (layout == TILE_CL || layout == TILE_CLQ) ? (long long)cells * cl_pitch(FG, layout)
+                                                                : (long long)cells * FG;
   return (int)((w + 3) & ~3ll);
 }
 
@@ -97,15 +102,34 @@ inline int tile_array_words(int cells, int FG, int layout) {
 //                                              their features are read with gaps
 // Whole-grid groups win as soon as a group holds >= 3 channels (or all of them); otherwise all channels in
 // balanced slabs of >= 3 rows; otherwise fewer channels in slabs.  halo = 1 for gathers (the +1 corner row).
-inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* out) {
+inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* out, bool allow_quad = false) {
   const int stride0 = s->dim == 2 ? s->size[1] : s->size[1] * s->size[2];
   const int W0 = s->size[0];
   const long long C = (long long)W0 * stride0;
   const int rows = W0 - halo;                  // base rows (gather) / destination rows (scatter)
   if (s->N > kTileMaxPoints) return false;
   const long long entries = (long long)s->N << s->dim;
-  // channel-last only pays when the per-entry work dwarfs the tile move (coarse, dense grids)
-  const int layout = entries >= 8 * C ? TILE_CL : ((stride0 % 4 == 0) ? TILE_PM4 : TILE_PM1);
+  // channel-last only pays when the per-entry work dwarfs the tile move (coarse, dense grids); its quad-lane form
+  // (CLQ: one lane = one point x 4 channels, 16-byte tile accesses) needs channel counts that are multiples of 4
+  const bool dense = entries >= 8 * C;
+  if (allow_quad && dense && s->F % 4 == 0 && s->F >= 8) {
+    const size_t lb = (((size_t)s->N + 7) & ~(size_t)7) * 2 + 32;
+    for (int FG = s->F; FG >= 8; FG -= 4) {
+      const size_t b = (size_t)tile_array_words((int)C, FG, TILE_CLQ) * 4 * arrays + lb;
+      if (b <= (size_t)kTileSmemTwoCtas) {
+        const int groups = (s->F + FG - 1) / FG;
+        FG = ((s->F + groups - 1) / groups + 3) & ~3;     // balanced groups, still multiples of 4
+        out->FG = FG;
+        out->R = rows;
+        out->slabs = 1;
+        out->layout = TILE_CLQ;
+        out->words = tile_array_words((int)C, FG, TILE_CLQ);
+        out->smem = (size_t)out->words * 4 * arrays + lb;
+        return true;
+      }
+    }
+  }
+  const int layout = dense ? TILE_CL : ((stride0 % 4 == 0) ? TILE_PM4 : TILE_PM1);
   const size_t list_bytes = (((size_t)s->N + 7) & ~(size_t)7) * 2 + 32;  // uint16 list + counters + mbarrier
   auto bytes = [&](long long cells, int FG) {
     return (size_t)tile_array_words((int)cells, FG, layout) * 4 * arrays + list_bytes;
@@ -203,12 +227,12 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
                     float* __restrict__ z, int* __restrict__ arg, Grid<D> g, int H, int F, int N, int FG, int R,
                     int slabs, int groups, int tw) {
   constexpr int S = 1 << D;
-  constexpr bool CL = LAYOUT == TILE_CL;
+  constexpr bool CL = LAYOUT == TILE_CL || LAYOUT == TILE_CLQ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int stride0 = g.stride[0];
   const int W0 = g.W[0];
   const int tile_cells = R * stride0;
-  const int cs = CL ? (FG | 1) : 1;             // word stride between cells
+  const int cs = CL ? cl_pitch(FG, LAYOUT) : 1; // word stride between cells
   const int fs = CL ? 1 : tile_cells;           // word stride between channels
   const bool want_arg = !SUM && arg != nullptr;
   float* tval = (float*)smem_raw;                                   // max: value bits   | sum: low limb
@@ -282,6 +306,62 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     }
   }
 
+  if constexpr (LAYOUT == TILE_CLQ && !SUM) {
+    // quad lanes: a lane owns one point and 4-channel quads q0, q0 + lpp, ... of it.  Lanes of a warp then cover
+    // 8 (or 16 / 32) points instead of 32, which divides the same-cell collisions of clustered clouds, and the
+    // arg pass reads the 4 tile values of a quad with one 16-byte shared load.
+    const int qn = fg >> 2;
+    const int lsh = qn >= 4 ? 2 : (qn >= 2 ? 1 : 0);
+    const int lpp = 1 << lsh;
+#pragma unroll 1
+    for (int pass = 0; pass < (want_arg ? 2 : 1); ++pass) {
+      for (int slot = threadIdx.x; slot < (cnt << lsh); slot += kTileThreads) {
+        const int n = slot >> lsh, q0 = slot & (lpp - 1);
+        const Pos<D> p = point_pos<D>(ku, n, N, g);
+        float w[S];
+        int a[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          w[s] = corner_weight<D>(p, s);
+          a[s] = (p.base + corner_offset<D>(g, s)) * cs;
+        }
+        const float pd = pu ? __ldg(pu + n) : 1.0f;
+        for (int q = q0; q < qn; q += lpp) {
+          const int f = q << 2;
+          float ft[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ft[j] = __ldg(fu + (size_t)(f + j) * N + n);
+            if (pu) ft[j] = CTB_FMUL(ft[j], pd);
+          }
+          if (pass == 0) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                atomicMax((int*)tval + a[s] + f + j, __float_as_int(fmaxf(CTB_FMUL(ft[j], w[s]), 0.0f)));
+          } else {
+            unsigned hits = 0;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const int4 t = *reinterpret_cast<const int4*>((const int*)tval + a[s] + f);
+              hits |= ((__float_as_int(CTB_FMUL(ft[0], w[s])) == t.x) & (t.x != 0)) ? (1u << (4 * s)) : 0u;
+              hits |= ((__float_as_int(CTB_FMUL(ft[1], w[s])) == t.y) & (t.y != 0)) ? (2u << (4 * s)) : 0u;
+              hits |= ((__float_as_int(CTB_FMUL(ft[2], w[s])) == t.z) & (t.z != 0)) ? (4u << (4 * s)) : 0u;
+              hits |= ((__float_as_int(CTB_FMUL(ft[3], w[s])) == t.w) & (t.w != 0)) ? (8u << (4 * s)) : 0u;
+            }
+            while (hits) {
+              const int b = __ffs(hits) - 1;
+              hits &= hits - 1;
+              const int sb = b >> 2;   // rare path: recompute the corner address instead of indexing registers
+              atomicMin((unsigned*)targ + (p.base + corner_offset<D>(g, sb)) * cs + f + (b & 3), (unsigned)(sb * N + n));
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  } else
 #pragma unroll 1
   for (int pass = 0; pass < (want_arg ? 2 : 1); ++pass) {
     for (int i = threadIdx.x; i < cnt; i += kTileThreads) {
@@ -427,7 +507,8 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
 }
 
 inline bool tile_scatter_config(const ctb_shape* s, bool sum, bool want_arg, TileConfig* out) {
-  return tile_config(s, (sum || want_arg) ? 2 : 1, 0, out);
+  // quad lanes measured faster only for the 3-D max scatter (c3d 0.43 -> 0.35 ms); 2-D and sum keep point lanes
+  return tile_config(s, (sum || want_arg) ? 2 : 1, 0, out, !sum && s->dim == 3);
 }
 
 template <int D, bool SUM, int LAYOUT>
@@ -463,6 +544,9 @@ cudaError_t tile_scatter(const float* keys, const float* feat, const float* pad,
     case TILE_PM1:
       return sum ? launch_tile_scatter<D, true, TILE_PM1>(keys, feat, pad, z, arg, s, c, stream)
                  : launch_tile_scatter<D, false, TILE_PM1>(keys, feat, pad, z, arg, s, c, stream);
+    case TILE_CLQ:
+      return sum ? launch_tile_scatter<D, true, TILE_CLQ>(keys, feat, pad, z, arg, s, c, stream)
+                 : launch_tile_scatter<D, false, TILE_CLQ>(keys, feat, pad, z, arg, s, c, stream);
     default:
       return sum ? launch_tile_scatter<D, true, TILE_CL>(keys, feat, pad, z, arg, s, c, stream)
                  : launch_tile_scatter<D, false, TILE_CL>(keys, feat, pad, z, arg, s, c, stream);
@@ -480,12 +564,12 @@ tile_gather_kernel(const float* __restrict__ keys, const float* __restrict__ t1,
                    const float* __restrict__ in, const float* __restrict__ pad, float* __restrict__ out,
                    float* __restrict__ grad_keys, Grid<D> g, int H, int F, int N, int FG, int R, int slabs, int tw) {
   constexpr int S = 1 << D;
-  constexpr bool CL = LAYOUT == TILE_CL;
+  constexpr bool CL = LAYOUT == TILE_CL || LAYOUT == TILE_CLQ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int stride0 = g.stride[0];
   const int W0 = g.W[0];
   const int tile_cells = (slabs == 1 ? W0 : R + 1) * stride0;
-  const int cs = CL ? (FG | 1) : 1;
+  const int cs = CL ? cl_pitch(FG, LAYOUT) : 1;
   const int fs = CL ? 1 : tile_cells;
   float* s1 = (float*)smem_raw;
   int* s2 = (int*)(s1 + tw);                                        // (SPLAT_BWD: arg)
@@ -537,6 +621,111 @@ tile_gather_kernel(const float* __restrict__ keys, const float* __restrict__ t1,
       });
       __syncthreads();
     }
+    if constexpr (LAYOUT == TILE_CLQ) {
+      // quad lanes (see tile_scatter_kernel): lane = (point, 4-channel quads q0, q0 + lpp, ...); 16-byte tile reads
+      const int qn = fg >> 2;
+      const int lsh = qn >= 4 ? 2 : (qn >= 2 ? 1 : 0);
+      const int lpp = 1 << lsh;
+#pragma unroll 1
+      for (int slot = threadIdx.x; slot < (cnt << lsh); slot += kTileThreads) {
+        const unsigned active = __activemask();
+        const int n = slot >> lsh, q0 = slot & (lpp - 1);
+        const Pos<D> p = point_pos<D>(ku, n, N, g);
+        const float pd = pu ? __ldg(pu + n) : 1.0f;
+        float w[S], gw[S];
+        int a[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          w[s] = corner_weight<D>(p, s);
+          a[s] = (p.base + corner_offset<D>(g, s) - cell0) * cs;
+          gw[s] = 0.0f;
+        }
+        for (int q = q0; q < qn; q += lpp) {
+          const int f = q << 2;
+          const size_t po = ((size_t)unit * F + f0 + f) * N + n;
+          if constexpr (MODE == GATHER_SLICE_FWD) {
+            float4 acc;
+            {
+              const float4 t = *reinterpret_cast<const float4*>(s1 + a[0] + f);
+              acc = make_float4(CTB_FMUL(t.x, w[0]), CTB_FMUL(t.y, w[0]), CTB_FMUL(t.z, w[0]), CTB_FMUL(t.w, w[0]));
+            }
+#pragma unroll
+            for (int s = 1; s < S; ++s) {
+              const float4 t = *reinterpret_cast<const float4*>(s1 + a[s] + f);
+              acc.x = fmaf(t.x, w[s], acc.x);
+              acc.y = fmaf(t.y, w[s], acc.y);
+              acc.z = fmaf(t.z, w[s], acc.z);
+              acc.w = fmaf(t.w, w[s], acc.w);
+            }
+            if (pu) {
+              acc.x = CTB_FMUL(acc.x, pd);
+              acc.y = CTB_FMUL(acc.y, pd);
+              acc.z = CTB_FMUL(acc.z, pd);
+              acc.w = CTB_FMUL(acc.w, pd);
+            }
+            out[po] = acc.x;
+            out[po + (size_t)N] = acc.y;
+            out[po + (size_t)2 * N] = acc.z;
+            out[po + (size_t)3 * N] = acc.w;
+          } else if constexpr (MODE == GATHER_SLICE_BWD_KEYS) {
+            float go[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              go[j] = __ldg(in + po + (size_t)j * N);
+              if (pu) go[j] *= pd;
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const float4 t = *reinterpret_cast<const float4*>(s1 + a[s] + f);
+              gw[s] = fmaf(t.x, go[0], gw[s]);
+              gw[s] = fmaf(t.y, go[1], gw[s]);
+              gw[s] = fmaf(t.z, go[2], gw[s]);
+              gw[s] = fmaf(t.w, go[3], gw[s]);
+            }
+          } else {
+            float ft[4], gf[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ft[j] = __ldg(in + po + (size_t)j * N);
+              if (pu) ft[j] *= pd;
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const int4 av = *reinterpret_cast<const int4*>(s2 + a[s] + f);
+              const float4 t = *reinterpret_cast<const float4*>(s1 + a[s] + f);
+              const int e = s * N + n;
+              const float g0 = av.x == e ? t.x : 0.0f, g1 = av.y == e ? t.y : 0.0f;
+              const float g2 = av.z == e ? t.z : 0.0f, g3 = av.w == e ? t.w : 0.0f;
+              gf[0] = fmaf(g0, w[s], gf[0]);
+              gf[1] = fmaf(g1, w[s], gf[1]);
+              gf[2] = fmaf(g2, w[s], gf[2]);
+              gf[3] = fmaf(g3, w[s], gf[3]);
+              gw[s] = fmaf(g0, ft[0], gw[s]);
+              gw[s] = fmaf(g1, ft[1], gw[s]);
+              gw[s] = fmaf(g2, ft[2], gw[s]);
+              gw[s] = fmaf(g3, ft[3], gw[s]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[po + (size_t)j * N] = pu ? gf[j] * pd : gf[j];
+          }
+        }
+        if constexpr (MODE != GATHER_SLICE_FWD) {
+          // fold the partial weight gradients of the point's lanes, one lane writes grad_keys
+          for (int o = 1; o < lpp; o <<= 1)
+#pragma unroll
+            for (int s = 0; s < S; ++s) gw[s] += __shfl_xor_sync(active, gw[s], o);
+          if (q0 == 0) {
+            float part[D];
+            weight_grad_to_key_grad<D>(p, gw, part);
+#pragma unroll
+            for (int a2 = 0; a2 < D; ++a2) {
+              float* gp = grad_keys + ((size_t)unit * D + a2) * N + n;
+              *gp = f0 == 0 ? part[a2] : *gp + part[a2];
+            }
+          }
+        }
+      }
+    } else
 #pragma unroll 1
     for (int i = threadIdx.x; i < cnt; i += kTileThreads) {
       const int n = slabs > 1 ? (int)sel[i] : i;
@@ -602,7 +791,8 @@ tile_gather_kernel(const float* __restrict__ keys, const float* __restrict__ t1,
 }
 
 inline bool gather_config(const ctb_shape* s, int mode, TileConfig* out) {
-  return tile_config(s, mode == GATHER_SPLAT_BWD ? 2 : 1, 1, out);
+  // quad lanes measured faster only for the 3-D Slice forward (c3d 0.16 -> 0.13 ms)
+  return tile_config(s, mode == GATHER_SPLAT_BWD ? 2 : 1, 1, out, mode == GATHER_SLICE_FWD && s->dim == 3);
 }
 
 template <int D, int MODE, int LAYOUT>
@@ -627,6 +817,7 @@ cudaError_t tile_gather(const float* keys, const float* t1, const int* t2, const
   switch (effective_layout(c.layout, t1, t2)) {
     case TILE_PM4: return launch_gather<D, MODE, TILE_PM4>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
     case TILE_PM1: return launch_gather<D, MODE, TILE_PM1>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
+    case TILE_CLQ: return launch_gather<D, MODE, TILE_CLQ>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
     default: return launch_gather<D, MODE, TILE_CL>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
   }
 }

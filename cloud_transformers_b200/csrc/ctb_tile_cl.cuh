@@ -30,7 +30,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
                   int tw, int LP) {
   constexpr int S = 1 << D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int fgp = FG | 1;
+  const int fgp = cl_pitch(FG, TILE_CL);
   const bool want_arg = !SUM && arg != nullptr;
   float* tval = (float*)smem_raw;                                    // max: value bits   | sum: low limb
   int* targ = (int*)(tval + tw);                                     // max: arg (if any) | sum: high limb
@@ -204,7 +204,7 @@ bool cl_scatter_try(const float* keys, const float* feat, const float* pad, floa
                     bool sum, cudaStream_t stream, cudaError_t* err) {
   TileConfig c;
   if (!tile_scatter_config(s, sum, arg != nullptr, &c)) return false;
-  if (c.layout != TILE_CL || c.slabs != 1) return false;
+  if ((c.layout != TILE_CL && c.layout != TILE_CLQ) || c.slabs != 1) return false;
   const int arrays = (sum || arg != nullptr) ? 2 : 1;
   // re-fit the channel group with the staging buffers included
   int FG = c.FG > 32 ? 32 : c.FG;
