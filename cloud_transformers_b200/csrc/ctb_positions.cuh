@@ -107,6 +107,22 @@ CTB_HD Pos<D> point_pos(const float* __restrict__ keys_u, int n, int N, const Gr
   return p;
 }
 
+// same as point_pos, from key values already in registers
+template <int D>
+CTB_HD Pos<D> point_pos_from_values(const float* kv, const Grid<D>& g) {
+  Pos<D> p;
+  int base = 0;
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    int c;
+    axis_pos<D>(kv[a], g.scale[a], g.W[a], p.up[a], p.dn[a], c, p.in_range[a]);
+    base += c * g.stride[a];
+    if (a == 0) p.c0 = c;
+  }
+  p.base = base;
+  return p;
+}
+
 // weight of corner s: left-associated product over axes, exactly as the reference multiplies.
 template <int D>
 CTB_HD float corner_weight(const Pos<D>& p, int s) {

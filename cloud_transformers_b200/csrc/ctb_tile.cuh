@@ -306,7 +306,90 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     }
   }
 
-  if constexpr (LAYOUT == TILE_CLQ && !SUM) {
+  if (!CL && slabs > 1 && cnt <= kTileThreads && fg <= 4) {
+    // Sparse-grid slab (class a): at most one point per thread.  All global loads (keys, features) are issued up
+    // front in one batch, and the arg pass reuses the registers of the max pass -- no second trip to L2.
+    const bool has = (int)threadIdx.x < cnt;
+    const int n = has ? (int)sel[threadIdx.x] : 0;
+    float kv[D], ft[4];
+#pragma unroll
+    for (int a2 = 0; a2 < D; ++a2) kv[a2] = __ldg(ku + (size_t)a2 * N + n);
+    const float pd = pu ? __ldg(pu + n) : 1.0f;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      ft[f] = f < fg ? __ldg(fu + (size_t)f * N + n) : 0.0f;
+      if (pu) ft[f] = CTB_FMUL(ft[f], pd);
+    }
+    const Pos<D> p = point_pos_from_values<D>(kv, g);
+    const bool in0 = has && (p.c0 >= x0) && (p.c0 < x1);
+    const bool in1 = has && (p.c0 + 1 >= x0) && (p.c0 + 1 < x1);
+    float w[S];
+    int a[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const bool ins = (s & 1) ? in1 : in0;
+      const int lc = p.base + corner_offset<D>(g, ins ? s : (s ^ 1)) - cell0;
+      w[s] = ins ? corner_weight<D>(p, s) : 0.0f;
+      a[s] = has ? lc : 0;
+    }
+    if constexpr (SUM) {
+      if (!has) {
+        // idle lanes must not touch the tile (they would all hammer word 0)
+      } else if (fixed_point && limb_bits > 0) {
+        const unsigned lmask = (1u << limb_bits) - 1u;
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          if (f < fg)
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+              if (w[s] != 0.0f) {
+                const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(ft[f], w[s]), scale));
+                atomicAdd((unsigned*)tval + a[s] + f * fs, (unsigned)q & lmask);
+                atomicAdd(targ + a[s] + f * fs, (int)(q >> limb_bits));
+              }
+      } else {
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          if (f < fg)
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+              if (w[s] != 0.0f) {
+                if (fixed_point) {
+                  const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(ft[f], w[s]), scale));
+                  const unsigned lo = (unsigned)q;
+                  const unsigned old = atomicAdd((unsigned*)tval + a[s] + f * fs, lo);
+                  const int hi = (int)(q >> 32) + ((unsigned)(old + lo) < old ? 1 : 0);
+                  if (hi != 0) atomicAdd(targ + a[s] + f * fs, hi);
+                } else {
+                  atomicAdd(tval + a[s] + f * fs, CTB_FMUL(ft[f], w[s]));
+                }
+              }
+      }
+      __syncthreads();
+    } else {
+      if (has) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          if (f < fg)
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+              atomicMax((int*)tval + a[s] + f * fs, __float_as_int(fmaxf(CTB_FMUL(ft[f], w[s]), 0.0f)));
+      }
+      __syncthreads();
+      if (want_arg) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          if (f < fg && has)
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const int t = ((const int*)tval)[a[s] + f * fs];
+              if ((__float_as_int(CTB_FMUL(ft[f], w[s])) == t) & (t != 0))
+                atomicMin((unsigned*)targ + a[s] + f * fs, (unsigned)(s * N + n));
+            }
+        __syncthreads();
+      }
+    }
+  } else if constexpr (LAYOUT == TILE_CLQ && !SUM) {
     // quad lanes: a lane owns one point and 4-channel quads q0, q0 + lpp, ... of it.  Lanes of a warp then cover
     // 8 (or 16 / 32) points instead of 32, which divides the same-cell collisions of clustered clouds, and the
     // arg pass reads the 4 tile values of a quad with one 16-byte shared load.
