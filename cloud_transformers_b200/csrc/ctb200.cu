@@ -163,7 +163,7 @@ int slice_bwd_atomic_impl(ctb::PointSource src, const float* grid, const float* 
 template <int D>
 cudaError_t tile_scatter_any(const float* keys, const float* feat, const float* pad, float* z, int* arg,
                              const ctb_shape* s, bool sum, cudaStream_t stream) {
-  static const bool no_cl = getenv("CTB_NO_CHANNEL_LANE") != nullptr;
+  static const bool no_cl = getenv("CTB_NO_CHANNEL_LANE") != nullptr || getenv("CTB_QUAD_SUM") != nullptr;
   cudaError_t e = cudaSuccess;
   // measured (profiles/r01_*): lanes = channels wins for the contended float-sum atomics (c3d 0.52 -> 0.32 ms) but
   // not for max, whose second pass is broadcast-friendly shared loads

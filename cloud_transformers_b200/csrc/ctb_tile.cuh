@@ -183,21 +183,31 @@ __device__ __forceinline__ int compact_slab_points(const float* __restrict__ ku,
   if (threadIdx.x == 0) *counter = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  for (int n0 = 0; n0 < N; n0 += kTileThreads) {
-    const int n = n0 + threadIdx.x;
-    bool take = false;
-    if (n < N) {
-      bool in_rng;
-      float up0, dn0;
-      int c0;
-      axis_pos<D>(__ldg(ku + n), g.scale[0], g.W[0], up0, dn0, c0, in_rng);
-      take = (c0 >= x0 && c0 < x1) || (BOTH_ROWS && (c0 + 1 >= x0 && c0 + 1 < x1));
+  constexpr int kBatch = 4;   // keys of 4 rounds are fetched together: one L2 round trip instead of four
+  for (int n0 = 0; n0 < N; n0 += kTileThreads * kBatch) {
+    float kx[kBatch];
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int n = n0 + b * kTileThreads + threadIdx.x;
+      kx[b] = n < N ? __ldg(ku + n) : 0.0f;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, take);
-    int base = 0;
-    if (lane == 0 && m) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (take) sel[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)n;
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int n = n0 + b * kTileThreads + threadIdx.x;
+      bool take = false;
+      if (n < N) {
+        bool in_rng;
+        float up0, dn0;
+        int c0;
+        axis_pos<D>(kx[b], g.scale[0], g.W[0], up0, dn0, c0, in_rng);
+        take = (c0 >= x0 && c0 < x1) || (BOTH_ROWS && (c0 + 1 >= x0 && c0 + 1 < x1));
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      int base = 0;
+      if (lane == 0 && m) base = atomicAdd(counter, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (take) sel[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)n;
+    }
   }
   __syncthreads();
   return *counter;
@@ -389,7 +399,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
         __syncthreads();
       }
     }
-  } else if constexpr (LAYOUT == TILE_CLQ && !SUM) {
+  } else if constexpr (LAYOUT == TILE_CLQ) {
     // quad lanes: a lane owns one point and 4-channel quads q0, q0 + lpp, ... of it.  Lanes of a warp then cover
     // 8 (or 16 / 32) points instead of 32, which divides the same-cell collisions of clustered clouds, and the
     // arg pass reads the 4 tile values of a quad with one 16-byte shared load.
@@ -417,7 +427,34 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
             ft[j] = __ldg(fu + (size_t)(f + j) * N + n);
             if (pu) ft[j] = CTB_FMUL(ft[j], pd);
           }
-          if (pass == 0) {
+          if constexpr (SUM) {
+            if (fixed_point && limb_bits > 0) {
+              const unsigned lmask = (1u << limb_bits) - 1u;
+#pragma unroll
+              for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(ft[j], w[s]), scale));
+                  atomicAdd((unsigned*)tval + a[s] + f + j, (unsigned)q & lmask);
+                  atomicAdd(targ + a[s] + f + j, (int)(q >> limb_bits));
+                }
+            } else {
+#pragma unroll
+              for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (fixed_point) {
+                    const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(ft[j], w[s]), scale));
+                    const unsigned lo = (unsigned)q;
+                    const unsigned old = atomicAdd((unsigned*)tval + a[s] + f + j, lo);
+                    const int hi = (int)(q >> 32) + ((unsigned)(old + lo) < old ? 1 : 0);
+                    if (hi != 0) atomicAdd(targ + a[s] + f + j, hi);
+                  } else {
+                    atomicAdd(tval + a[s] + f + j, CTB_FMUL(ft[j], w[s]));
+                  }
+                }
+            }
+          } else if (pass == 0) {
 #pragma unroll
             for (int s = 0; s < S; ++s)
 #pragma unroll
@@ -591,7 +628,8 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
 
 inline bool tile_scatter_config(const ctb_shape* s, bool sum, bool want_arg, TileConfig* out) {
   // quad lanes measured faster only for the 3-D max scatter (c3d 0.43 -> 0.35 ms); 2-D and sum keep point lanes
-  return tile_config(s, (sum || want_arg) ? 2 : 1, 0, out, !sum && s->dim == 3);
+  static const bool quad_sum = getenv("CTB_QUAD_SUM") != nullptr;
+  return tile_config(s, (sum || want_arg) ? 2 : 1, 0, out, (!sum || quad_sum) && s->dim == 3);
 }
 
 template <int D, bool SUM, int LAYOUT>
