@@ -223,10 +223,14 @@ def run_ours(args):
 
     # ---- e2e through the public modules with host buffers -----------------------------------------
     e2e = run_e2e(args, dev, world, rank, data, order)
+    ref_gpu = reference_composition_on_gpu(dev, data) if rank == 0 else None
+    n_launches = args.steps * sum(paths[n].launches_per_pass() for n, _, _, _ in order)
+    del data, paths
+    torch.cuda.empty_cache()
+    train = run_train(args, dev, world, rank) if args.train_steps > 0 else None
 
     if rank == 0:
         cpu = cpu_baseline(sample_batch=8, repeats=3)
-        ref_gpu = reference_composition_on_gpu(dev, data)
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
@@ -242,7 +246,8 @@ def run_ours(args):
                          "traffic": None, "share_of_step": round(top["ms"] / total_op_ms, 4)},
             "ops": ops,
             "e2e": e2e,
-            "gpu_launches": args.steps * sum(paths[n].launches_per_pass() for n, _, _, _ in order),
+            "train": train,
+            "gpu_launches": n_launches,
             "clocks": clocks,
             "cpu_baseline": cpu,
             "reference_composition_gpu": ref_gpu,
@@ -342,6 +347,64 @@ def reference_composition_on_gpu(dev, data):
         torch.cuda.empty_cache()
 
 
+def run_train(args, dev, world, rank):
+    """Second half of the BASELINE metric: MHCT training samples/s.  A ScanObjectNN-classifier-shaped trunk built from
+    the block mirrors (cloud_transformers_b200/mhct.py: 12 MultiHeadUnion + 2 MultiHeadPool, 24 Splat + 24 Slice + 2
+    pool Splats per forward, like model_zoo/scanobject/classifier.py), Adam, cross-entropy on synthetic labels, clouds
+    copied from pinned host memory every step; DDP + SyncBatchNorm over NCCL when world > 1 (what
+    train_classification.py:107-109 does).  Convolutions / BatchNorm / Linear are stock PyTorch."""
+    import torch
+    import torch.distributed as dist
+    from cloud_transformers_b200.mhct import ScanObjectTrunk
+    try:
+        torch.manual_seed(1234 + rank)
+        B = args.train_batch
+        model = ScanObjectTrunk().to(dev)
+        if world > 1:
+            model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index])
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        gen = torch.Generator(device=dev).manual_seed(7 + rank)
+        clouds = [surface_clouds(gen, B, N_PTS, dev).cpu().pin_memory() for _ in range(4)]
+        labels = [torch.randint(0, 15, (B,)).pin_memory() for _ in range(4)]
+        loss_host = torch.zeros(1).pin_memory()
+
+        def step(i):
+            pcd = clouds[i % 4].to(dev, non_blocking=True)
+            y = labels[i % 4].to(dev, non_blocking=True)
+            logits, _ = model(pcd)
+            loss = torch.nn.functional.cross_entropy(logits, y)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+        for i in range(3):
+            step(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.train_steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.train_steps
+        if world > 1:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        n_params = sum(p.numel() for p in model.parameters())
+        return {"samples_per_s": round(world * B / (ms * 1e-3), 2), "ms_per_step": round(ms, 2), "batch_per_gpu": B,
+                "points": N_PTS, "steps": args.train_steps, "params_m": round(n_params / 1e6, 2),
+                "final_loss": round(float(loss_host[0]), 4),
+                "model": "ScanObjectTrunk (classifier.py trunk: 12 MultiHeadUnion + 2 MultiHeadPool; towers -> avgpool)",
+                "parallelism": "dp%d (DDP + SyncBN over NCCL)" % world if world > 1 else "single GPU"}
+    except Exception as exc:
+        return {"unavailable": repr(exc)[:300]}
+
+
 def cpu_step(sample_batch, threads):
     """One bounded sample of the workload on the host: the six shape classes once each at batch
     `sample_batch` through the reference's torch composition (oracle/ct_torch.py)."""
@@ -405,6 +468,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--train-steps", type=int, default=10, help="steps of the MHCT training throughput add-on (0 = skip)")
+    ap.add_argument("--train-batch", type=int, default=B_PER_GPU)
     ap.add_argument("--mode", default=os.environ.get("CTB_MODE", "auto"), choices=["auto", "atomic", "tile", "deterministic"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

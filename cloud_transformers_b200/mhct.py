@@ -137,3 +137,40 @@ class MultiHeadUnion(nn.Module):
             results.append(r)
             stats.append(s)
         return residual + self.after(torch.cat(results, dim=1)), stats
+
+
+class ScanObjectTrunk(nn.Module):
+    """The MHCT trunk of the reference's ScanObjectNN classifier (model_zoo/scanobject/classifier.py:41-85, :114-131):
+    Conv1d(3 -> 512) + BN + ReLU, 12 MultiHeadUnion blocks (4 x {2D 128^2 F4 + 3D 32^3 F4, 2D 64^2 F16 + 3D 16^3 F16,
+    2D 16^2 F16 + 3D 8^3 F32}, 16 heads each) and the two MultiHeadPool rasterisations (3D 8^3 F32, 2D 16^2 F16).
+    The Res2D/Res3D towers behind the pools (dense cuDNN convolutions, out of scope here) are replaced by a global
+    average pool + Linear so the trunk can be trained end to end; bench.py uses it for the MHCT training throughput."""
+
+    def __init__(self, n_classes=15, model_dim=512, n_rounds=4):
+        super().__init__()
+        self.model_dim = model_dim
+        self.first_process = nn.Sequential(nn.Conv1d(3, model_dim, kernel_size=1, bias=False), nn.BatchNorm1d(model_dim),
+                                           nn.ReLU(inplace=True))
+        blocks = []
+        for _ in range(n_rounds):
+            for feats, sizes in (([4, 4], [128, 32]), ([16, 16], [64, 16]), ([16, 32], [16, 8])):
+                blocks.append(MultiHeadUnion(model_dim=model_dim, features_dims=feats, heads=[16, 16], tensor_sizes=sizes,
+                                             model_dim_out=model_dim, tensor_dims=[2, 3]))
+        self.attentions_encoder = nn.ModuleList(blocks)
+        self.pool3d = MultiHeadPool(model_dim=model_dim, in_feature_dim=32, heads=16, tensor_size=8, tensor_dim=3)
+        self.pool2d = MultiHeadPool(model_dim=model_dim, in_feature_dim=16, heads=16, tensor_size=16, tensor_dim=2)
+        self.class_vector = nn.Sequential(nn.Linear(32 * 16 + 16 * 16, 1024), nn.BatchNorm1d(1024), nn.ReLU(inplace=True))
+        self.class_head = nn.Sequential(nn.Dropout(0.5), nn.Linear(1024, n_classes))
+
+    def forward(self, pcd):
+        """pcd [B, 3, N] -> class logits [B, n_classes], list of per-block lattice statistics."""
+        x = self.first_process(pcd)
+        stats = []
+        for block in self.attentions_encoder:
+            x, st = block(x, pcd)
+            stats += st
+        to_3d, st3 = self.pool3d(x, pcd)
+        to_2d, st2 = self.pool2d(x, pcd)
+        stats += [st3, st2]
+        pooled = torch.cat([to_3d.flatten(2).mean(-1), to_2d.flatten(2).mean(-1)], dim=-1)
+        return self.class_head(self.class_vector(pooled)), stats
