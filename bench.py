@@ -116,10 +116,11 @@ def surface_clouds(gen, B, N, device):
     return pts.permute(0, 2, 1).contiguous()          # [B, 3, N]
 
 
-def make_class_inputs(gen, dim, W, F, B, device):
+def make_class_inputs(gen, dim, W, F, B, device, grid_dtype=None):
     """keys = tanh(per-head rotated + shifted cloud) (what MultiHead feeds DifferentiablePositions,
     multihead_ct.py:93-99), features ~ N(0,1), plus the conv output and the two incoming gradients."""
     import torch
+    grid_dtype = grid_dtype or torch.float32
     pcd = surface_clouds(gen, B, N_PTS, device)
     rot = torch.linalg.qr(torch.randn(H, 3, 3, generator=gen, device=device))[0]
     keys3 = torch.einsum("bcp,hcn->bhnp", pcd * 1.5, rot) + 0.05 * torch.randn(B, H, 3, N_PTS, generator=gen,
@@ -127,8 +128,8 @@ def make_class_inputs(gen, dim, W, F, B, device):
     keys = torch.tanh(keys3[:, :, :dim].reshape(B, H * dim, N_PTS)).contiguous()
     feat = torch.randn(B, H * F, N_PTS, generator=gen, device=device)
     grid_shape = (B, H * F) + (W,) * dim
-    conv = torch.randn(grid_shape, generator=gen, device=device)
-    gz = torch.randn(grid_shape, generator=gen, device=device)
+    conv = torch.randn(grid_shape, generator=gen, device=device).to(grid_dtype)
+    gz = torch.randn(grid_shape, generator=gen, device=device).to(grid_dtype)
     go = torch.randn(B, H * F, N_PTS, generator=gen, device=device)
     return keys, feat, conv, go, gz
 
@@ -152,12 +153,14 @@ def run_ours(args):
     ctb.config.mode = args.mode
     gen = torch.Generator(device=dev).manual_seed(42 + rank)
     B = B_PER_GPU
+    gdt = torch.bfloat16 if args.grid_dtype == "bf16" else torch.float32
+    eg = 2 if args.grid_dtype == "bf16" else 4
     data, paths = {}, {}
     for name, dim, W, F in CLASSES:
-        data[name] = make_class_inputs(gen, dim, W, F, B, dev)
-        paths[name] = HotPath(W, H, dim, B, F, N_PTS, dev, mode=args.mode)
+        data[name] = make_class_inputs(gen, dim, W, F, B, dev, gdt)
+        paths[name] = HotPath(W, H, dim, B, F, N_PTS, dev, mode=args.mode, grid_dtype=gdt)
     order = [c for _ in range(REPEATS) for c in CLASSES]          # same class never back to back => L2 is cold
-    step_bytes = sum(algorithmic_bytes(N_PTS, dim, F, W ** dim)["total"] * B * H for _, dim, W, F in order)
+    step_bytes = sum(algorithmic_bytes(N_PTS, dim, F, W ** dim, e_grid=eg)["total"] * B * H for _, dim, W, F in order)
     pt_heads_step = len(order) * B * H * N_PTS
 
     def step():
@@ -199,7 +202,7 @@ def run_ours(args):
     for name, dim, W, F in CLASSES:
         keys, feat, conv, go, gz = data[name]
         hp = paths[name]
-        ab = algorithmic_bytes(N_PTS, dim, F, W ** dim)
+        ab = algorithmic_bytes(N_PTS, dim, F, W ** dim, e_grid=eg)
         calls = {"splat_fwd": lambda: hp.splat_fwd(keys, feat), "slice_fwd": lambda: hp.slice_fwd(keys, conv),
                  "slice_bwd": lambda: hp.slice_bwd(keys, conv, go), "splat_bwd": lambda: hp.splat_bwd(keys, feat, gz)}
         for op, fn in calls.items():
@@ -234,7 +237,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.grid_dtype == "f32" else "f32 arithmetic, bf16 grid storage", "data": "synthetic",
             "config": {"workload": "scanobjectnn_hotpath", "blocks_per_step": len(order), "batch_per_gpu": B,
                        "heads": H, "points": N_PTS, "classes": [c[0] for c in CLASSES], "mode": args.mode,
                        "l2": "working set per step %.1f GB >> 126 MB L2; same class never back to back" %
@@ -275,7 +279,8 @@ def run_e2e(args, dev, world, rank, data, order):
     mods, host = {}, {}
     for name, dim, W, F in CLASSES:
         mods[name] = (ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim).to(dev),
-                      ctb.Splat(tensor_size=W, heads=H, dim=dim).to(dev),
+                      ctb.Splat(tensor_size=W, heads=H, dim=dim,
+                                out_dtype=torch.bfloat16 if args.grid_dtype == "bf16" else None).to(dev),
                       ctb.Slice(tensor_size=W, heads=H, dim=dim).to(dev))
         keys, feat = data[name][0], data[name][1]
         host[name] = (keys.cpu().pin_memory(), feat.cpu().pin_memory())
@@ -470,6 +475,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--train-steps", type=int, default=10, help="steps of the MHCT training throughput add-on (0 = skip)")
     ap.add_argument("--train-batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--grid-dtype", default="f32", choices=["f32", "bf16"],
+                    help="bf16: grids (z, convolved, grad_grid, grad_z) stored as bf16, arithmetic stays fp32")
     ap.add_argument("--mode", default=os.environ.get("CTB_MODE", "auto"), choices=["auto", "atomic", "tile", "deterministic"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

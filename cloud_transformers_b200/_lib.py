@@ -20,11 +20,12 @@ CTB_ERR_WORKSPACE = -4
 REDUCE_MAX, REDUCE_SUM = 0, 1
 MODE_ATOMIC, MODE_DETERMINISTIC, MODE_TILE = 0, 1, 2
 OP_SPLAT_FWD, OP_SPLAT_BWD, OP_SLICE_FWD, OP_SLICE_BWD = 0, 1, 2, 3
+DTYPE_F32, DTYPE_BF16 = 0, 1
 
 
 class CtbShape(ctypes.Structure):
     _fields_ = [("B", ctypes.c_int32), ("H", ctypes.c_int32), ("F", ctypes.c_int32), ("N", ctypes.c_int32),
-                ("dim", ctypes.c_int32), ("size", ctypes.c_int32 * 3)]
+                ("dim", ctypes.c_int32), ("size", ctypes.c_int32 * 3), ("grid_dtype", ctypes.c_int32)]
 
 
 class CtbError(RuntimeError):
@@ -85,9 +86,10 @@ def load():
     return _lib
 
 
-def make_shape(B, H, F, N, dim, size):
+def make_shape(B, H, F, N, dim, size, grid_dtype=0):
     s = CtbShape()
     s.B, s.H, s.F, s.N, s.dim = int(B), int(H), int(F), int(N), int(dim)
+    s.grid_dtype = int(grid_dtype)
     for a in range(3):
         s.size[a] = int(size[a]) if a < len(size) else 1
     return s

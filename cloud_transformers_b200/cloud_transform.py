@@ -94,10 +94,11 @@ class Splat(DifferentiableGridModule):
 
     reduce="max" is the reference (scatter_max onto a zero grid); reduce="sum" is the scatter-add variant.'''
 
-    def __init__(self, tensor_size=20, heads=4, dim=3, reduce="max"):
+    def __init__(self, tensor_size=20, heads=4, dim=3, reduce="max", out_dtype=None):
         super().__init__(tensor_size, heads, dim)
         assert reduce in ("max", "sum")
         self.reduce = reduce
+        self.out_dtype = out_dtype      # torch.bfloat16: bf16 grid storage mode (extension; reference returns fp32)
 
     def forward(self, local_coordinate, flattened_index, features, pts_padding=None):
         '''
@@ -108,8 +109,9 @@ class Splat(DifferentiableGridModule):
         reduce = _lib.REDUCE_MAX if self.reduce == "max" else _lib.REDUCE_SUM
         handle = _handle_of(local_coordinate, flattened_index)
         if handle is not None and handle.geom.sizes == self._geom.sizes and handle.geom.heads == self.heads:
-            return CF.fused_splat(handle, features, pts_padding, reduce)
-        return CF.splat(local_coordinate, flattened_index, features, pts_padding, self._geom, reduce)
+            return CF.fused_splat(handle, features, pts_padding, reduce, self.out_dtype)
+        z = CF.splat(local_coordinate, flattened_index, features, pts_padding, self._geom, reduce)
+        return z if self.out_dtype is None else z.to(self.out_dtype)
 
 
 class Slice(DifferentiableGridModule):

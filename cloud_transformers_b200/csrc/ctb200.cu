@@ -41,6 +41,7 @@ int check_shape(const ctb_shape* s, bool need_f) {
   if (s->B <= 0 || s->H <= 0 || s->N <= 0) return CTB_ERR_INVALID_ARGUMENT;
   if (need_f && s->F <= 0) return CTB_ERR_INVALID_ARGUMENT;
   if (s->dim != 2 && s->dim != 3) return CTB_ERR_INVALID_ARGUMENT;
+  if (s->grid_dtype != CTB_DTYPE_F32 && s->grid_dtype != CTB_DTYPE_BF16) return CTB_ERR_INVALID_ARGUMENT;
   long long C = 1;
   for (int a = 0; a < s->dim; ++a) {
     if (s->size[a] < 2) return CTB_ERR_INVALID_ARGUMENT;
@@ -160,15 +161,38 @@ int slice_bwd_atomic_impl(ctb::PointSource src, const float* grid, const float* 
 }
 
 // TILE-mode scatter: channel-lane kernel for coarse dense grids, point-lane kernel otherwise
-template <int D>
-cudaError_t tile_scatter_any(const float* keys, const float* feat, const float* pad, float* z, int* arg,
+template <int D, typename GT>
+cudaError_t tile_scatter_any(const float* keys, const float* feat, const float* pad, GT* z, int* arg,
                              const ctb_shape* s, bool sum, cudaStream_t stream) {
   static const bool no_cl = getenv("CTB_NO_CHANNEL_LANE") != nullptr || getenv("CTB_QUAD_SUM") != nullptr;
   cudaError_t e = cudaSuccess;
   // measured (profiles/r01_*): lanes = channels wins for the contended float-sum atomics (c3d 0.52 -> 0.32 ms) but
   // not for max, whose second pass is broadcast-friendly shared loads
-  if (!no_cl && sum && ctb::cl_scatter_try<D>(keys, feat, pad, z, arg, s, sum, stream, &e)) return e;
-  return ctb::tile_scatter<D>(keys, feat, pad, z, arg, s, sum, stream);
+  if (!no_cl && sum && ctb::cl_scatter_try<D, GT>(keys, feat, pad, z, arg, s, sum, stream, &e)) return e;
+  return ctb::tile_scatter<D, GT>(keys, feat, pad, z, arg, s, sum, stream);
+}
+
+// dimension x grid-dtype dispatch for the tile kernels
+typedef __nv_bfloat16 bf16_t;
+inline cudaError_t scatter_dispatch(const float* keys, const float* feat, const float* pad, void* z, int* arg,
+                                    const ctb_shape* s, bool sum, cudaStream_t st) {
+  const bool bf = s->grid_dtype == CTB_DTYPE_BF16;
+  if (s->dim == 2)
+    return bf ? tile_scatter_any<2, bf16_t>(keys, feat, pad, (bf16_t*)z, arg, s, sum, st)
+              : tile_scatter_any<2, float>(keys, feat, pad, (float*)z, arg, s, sum, st);
+  return bf ? tile_scatter_any<3, bf16_t>(keys, feat, pad, (bf16_t*)z, arg, s, sum, st)
+            : tile_scatter_any<3, float>(keys, feat, pad, (float*)z, arg, s, sum, st);
+}
+
+template <int MODE>
+cudaError_t gather_dispatch(const float* keys, const void* t1, const int* t2, const float* in, const float* pad,
+                            float* out, float* grad_keys, const ctb_shape* s, cudaStream_t st) {
+  const bool bf = s->grid_dtype == CTB_DTYPE_BF16;
+  if (s->dim == 2)
+    return bf ? ctb::tile_gather<2, MODE, bf16_t>(keys, (const bf16_t*)t1, t2, in, pad, out, grad_keys, s, st)
+              : ctb::tile_gather<2, MODE, float>(keys, (const float*)t1, t2, in, pad, out, grad_keys, s, st);
+  return bf ? ctb::tile_gather<3, MODE, bf16_t>(keys, (const bf16_t*)t1, t2, in, pad, out, grad_keys, s, st)
+            : ctb::tile_gather<3, MODE, float>(keys, (const float*)t1, t2, in, pad, out, grad_keys, s, st);
 }
 
 #define CTB_DISPATCH_DIM(shape, call2, call3) ((shape)->dim == 2 ? (call2) : (call3))
@@ -299,13 +323,15 @@ int ctb_plan_build(const float* keys, void* plan, size_t plan_bytes, const ctb_s
                                      : ctb::sorted_plan_build<3>(keys, plan, shape, (cudaStream_t)stream));
 }
 
-int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pad, float* z, int32_t* arg,
+int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pad, void* z_any, int32_t* arg,
                        const ctb_shape* shape, int reduce, int mode, const void* plan, void* stream) {
+  float* z = (float*)z_any;
   int st = check_shape(shape, true);
   if (st) return st;
   if (!keys || !features || !z) return CTB_ERR_INVALID_ARGUMENT;
   if (reduce != CTB_REDUCE_MAX && reduce != CTB_REDUCE_SUM) return CTB_ERR_INVALID_ARGUMENT;
   if (reduce == CTB_REDUCE_MAX && !arg) return CTB_ERR_INVALID_ARGUMENT;
+  if (shape->grid_dtype != CTB_DTYPE_F32 && mode != CTB_MODE_TILE) return CTB_ERR_UNSUPPORTED;
   if (mode == CTB_MODE_DETERMINISTIC) {
     if (!plan) return CTB_ERR_WORKSPACE;
     const bool sum = reduce == CTB_REDUCE_SUM;
@@ -315,9 +341,7 @@ int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pa
   }
   if (mode == CTB_MODE_TILE) {
     const bool sum = reduce == CTB_REDUCE_SUM;
-    return cuda_status(shape->dim == 2
-                           ? tile_scatter_any<2>(keys, features, pad, z, sum ? nullptr : arg, shape, sum, (cudaStream_t)stream)
-                           : tile_scatter_any<3>(keys, features, pad, z, sum ? nullptr : arg, shape, sum, (cudaStream_t)stream));
+    return cuda_status(scatter_dispatch(keys, features, pad, z_any, sum ? nullptr : arg, shape, sum, (cudaStream_t)stream));
   }
   if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;
   ctb::PointSource src{keys, nullptr, nullptr};
@@ -326,9 +350,10 @@ int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pa
                           (splat_fwd_atomic_impl<3, true>(src, features, pad, z, arg, shape, reduce, stream)));
 }
 
-int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pad, const float* grad_z,
+int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pad, const void* grad_z_any,
                        const int32_t* arg, float* grad_features, float* grad_keys, const ctb_shape* shape,
                        int reduce, int mode, void* stream) {
+  const float* grad_z = (const float*)grad_z_any;
   int st = check_shape(shape, true);
   if (st) return st;
   if (!keys || !features || !grad_z || !grad_features || !grad_keys) return CTB_ERR_INVALID_ARGUMENT;
@@ -336,12 +361,10 @@ int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pa
   if (reduce == CTB_REDUCE_MAX && !arg) return CTB_ERR_INVALID_ARGUMENT;
   if (mode == CTB_MODE_DETERMINISTIC || mode == CTB_MODE_TILE) {
     if (reduce != CTB_REDUCE_MAX) return CTB_ERR_UNSUPPORTED;
-    return cuda_status(shape->dim == 2
-                           ? (ctb::tile_gather<2, ctb::GATHER_SPLAT_BWD>(keys, grad_z, arg, features, pad, grad_features,
-                                                                        grad_keys, shape, (cudaStream_t)stream))
-                           : (ctb::tile_gather<3, ctb::GATHER_SPLAT_BWD>(keys, grad_z, arg, features, pad, grad_features,
-                                                                        grad_keys, shape, (cudaStream_t)stream)));
+    return cuda_status(gather_dispatch<ctb::GATHER_SPLAT_BWD>(keys, grad_z_any, arg, features, pad, grad_features,
+                                                               grad_keys, shape, (cudaStream_t)stream));
   }
+  if (shape->grid_dtype != CTB_DTYPE_F32) return CTB_ERR_UNSUPPORTED;
   if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;
   ctb::PointSource src{keys, nullptr, nullptr};
   return CTB_DISPATCH_DIM(
@@ -350,26 +373,27 @@ int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pa
       (splat_bwd_impl<3, true>(src, features, pad, grad_z, arg, grad_features, grad_keys, shape, reduce, stream)));
 }
 
-int ctb_slice_fwd_keys(const float* keys, const float* grid, const float* pad, float* out,
+int ctb_slice_fwd_keys(const float* keys, const void* grid_any, const float* pad, float* out,
                        const ctb_shape* shape, int mode, void* stream) {
+  const float* grid = (const float*)grid_any;
   int st = check_shape(shape, true);
   if (st) return st;
   if (!keys || !grid || !out) return CTB_ERR_INVALID_ARGUMENT;
   if (mode == CTB_MODE_DETERMINISTIC || mode == CTB_MODE_TILE)
-    return cuda_status(shape->dim == 2
-                           ? (ctb::tile_gather<2, ctb::GATHER_SLICE_FWD>(keys, grid, nullptr, nullptr, pad, out, nullptr,
-                                                                        shape, (cudaStream_t)stream))
-                           : (ctb::tile_gather<3, ctb::GATHER_SLICE_FWD>(keys, grid, nullptr, nullptr, pad, out, nullptr,
-                                                                        shape, (cudaStream_t)stream)));
+    return cuda_status(gather_dispatch<ctb::GATHER_SLICE_FWD>(keys, grid_any, nullptr, nullptr, pad, out, nullptr, shape,
+                                                               (cudaStream_t)stream));
+  if (shape->grid_dtype != CTB_DTYPE_F32) return CTB_ERR_UNSUPPORTED;
   if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;
   ctb::PointSource src{keys, nullptr, nullptr};
   return CTB_DISPATCH_DIM(shape, (slice_fwd_impl<2, true>(src, grid, pad, out, shape, stream)),
                           (slice_fwd_impl<3, true>(src, grid, pad, out, shape, stream)));
 }
 
-int ctb_slice_bwd_keys(const float* keys, const float* grid, const float* pad, const float* grad_out,
-                       float* grad_grid, float* grad_keys, const ctb_shape* shape, int mode, const void* plan,
+int ctb_slice_bwd_keys(const float* keys, const void* grid_any, const float* pad, const float* grad_out,
+                       void* grad_grid_any, float* grad_keys, const ctb_shape* shape, int mode, const void* plan,
                        void* stream) {
+  const float* grid = (const float*)grid_any;
+  float* grad_grid = (float*)grad_grid_any;
   int st = check_shape(shape, true);
   if (st) return st;
   if (!keys || !grid || !grad_out || !grad_grid || !grad_keys) return CTB_ERR_INVALID_ARGUMENT;
@@ -378,22 +402,19 @@ int ctb_slice_bwd_keys(const float* keys, const float* grid, const float* pad, c
     // grad_grid: scatter-add of grad_out * pad (the Splat-sum kernel of the mode) ...
     if (mode == CTB_MODE_DETERMINISTIC) {
       if (!plan) return CTB_ERR_WORKSPACE;
+      if (shape->grid_dtype != CTB_DTYPE_F32) return CTB_ERR_UNSUPPORTED;
       st = cuda_status(shape->dim == 2
                            ? ctb::sorted_scatter<2>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream)
                            : ctb::sorted_scatter<3>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream));
     } else {
-      st = cuda_status(shape->dim == 2
-                           ? tile_scatter_any<2>(keys, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream)
-                           : tile_scatter_any<3>(keys, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream));
+      st = cuda_status(scatter_dispatch(keys, grad_out, pad, grad_grid_any, nullptr, shape, true, (cudaStream_t)stream));
     }
     if (st) return st;
     // ... and grad_keys: tile gather against the convolved grid.
-    return cuda_status(shape->dim == 2
-                           ? (ctb::tile_gather<2, ctb::GATHER_SLICE_BWD_KEYS>(keys, grid, nullptr, grad_out, pad, nullptr,
-                                                                             grad_keys, shape, (cudaStream_t)stream))
-                           : (ctb::tile_gather<3, ctb::GATHER_SLICE_BWD_KEYS>(keys, grid, nullptr, grad_out, pad, nullptr,
-                                                                             grad_keys, shape, (cudaStream_t)stream)));
+    return cuda_status(gather_dispatch<ctb::GATHER_SLICE_BWD_KEYS>(keys, grid_any, nullptr, grad_out, pad, nullptr,
+                                                                    grad_keys, shape, (cudaStream_t)stream));
   }
+  if (shape->grid_dtype != CTB_DTYPE_F32) return CTB_ERR_UNSUPPORTED;
   if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;
   ctb::PointSource src{keys, nullptr, nullptr};
   return CTB_DISPATCH_DIM(

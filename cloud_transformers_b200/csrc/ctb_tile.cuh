@@ -26,9 +26,11 @@
 //                      half of A5 Slice backward (reduce = sum, shared float atomics).
 // tile_gather_kernel   A4 Slice forward, the grad_keys half of A5, A6 Splat backward (+A7 folded in).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "../../include/ctb200.h"
 #include "ctb_positions.cuh"
 
@@ -76,6 +78,12 @@ __device__ __forceinline__ void bulk_commit_and_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// grid element type GT: float, or __nv_bfloat16 for the bf16 STORAGE mode (grids in bf16, all arithmetic in fp32)
+__device__ __forceinline__ float grid_load(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float grid_load(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void grid_store(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void grid_store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
 struct TileConfig {
   int FG;      // channels per tile
@@ -231,13 +239,14 @@ __device__ __forceinline__ void for_each_plane_element(int fg, int count, Fn fn)
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int D, bool SUM, int LAYOUT>
+template <int D, bool SUM, int LAYOUT, typename GT>
 __global__ void __launch_bounds__(kTileThreads, 2)
 tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat, const float* __restrict__ pad,
-                    float* __restrict__ z, int* __restrict__ arg, Grid<D> g, int H, int F, int N, int FG, int R,
+                    GT* __restrict__ z, int* __restrict__ arg, Grid<D> g, int H, int F, int N, int FG, int R,
                     int slabs, int groups, int tw) {
   constexpr int S = 1 << D;
   constexpr bool CL = LAYOUT == TILE_CL || LAYOUT == TILE_CLQ;
+  constexpr bool F32 = std::is_same<GT, float>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int stride0 = g.stride[0];
   const int W0 = g.W[0];
@@ -581,15 +590,15 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   }
 
   // store the slab once, coalesced
-  float* zu = z + ((size_t)unit * F + f0) * g.C + cell0;
+  GT* zu = z + ((size_t)unit * F + f0) * g.C + cell0;
   int* au = want_arg ? arg + ((size_t)unit * F + f0) * g.C + cell0 : nullptr;
-  if constexpr (LAYOUT == TILE_PM4 && !SUM) {
+  if constexpr (LAYOUT == TILE_PM4 && !SUM && F32) {
     // the tile already holds the final bits of z (and arg): hand it to the copy engine, plane by plane
     fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) {
       for (int f = 0; f < fg; ++f) {
-        bulk_s2g(zu + (size_t)f * g.C, tval + (size_t)f * tile_cells, (uint32_t)ncell * 4u);
+        bulk_s2g((float*)zu + (size_t)f * g.C, tval + (size_t)f * tile_cells, (uint32_t)ncell * 4u);
         if (want_arg) bulk_s2g(au + (size_t)f * g.C, targ + (size_t)f * tile_cells, (uint32_t)ncell * 4u);
       }
       bulk_commit_and_wait_read();
@@ -601,7 +610,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     const long long q = limb_bits > 0 ? ((long long)hi << limb_bits) + lo : (((long long)hi << 32) | lo);
     return __ll2float_rn(q) * inv_scale;
   };
-  if constexpr (LAYOUT == TILE_PM4) {
+  if constexpr (LAYOUT == TILE_PM4 && F32) {
     for_each_plane_element(fg, ncell >> 2, [&](int f, int r) {
       float4 v4 = reinterpret_cast<const float4*>(tval + (size_t)f * tile_cells)[r];
       if (SUM && fixed_point) {
@@ -611,7 +620,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
         v4.z = limbs_to_float(v4.z, h4.z);
         v4.w = limbs_to_float(v4.w, h4.w);
       }
-      __stcs(reinterpret_cast<float4*>(zu + (size_t)f * g.C) + r, v4);
+      __stcs(reinterpret_cast<float4*>((float*)zu + (size_t)f * g.C) + r, v4);
       if (want_arg)
         __stcs(reinterpret_cast<int4*>(au + (size_t)f * g.C) + r,
                reinterpret_cast<const int4*>(targ + (size_t)f * tile_cells)[r]);
@@ -620,7 +629,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     for_each_plane_element(fg, ncell, [&](int f, int r) {
       float v1 = tval[r * cs + f * fs];
       if (SUM && fixed_point) v1 = limbs_to_float(v1, targ[r * cs + f * fs]);
-      __stcs(zu + (size_t)f * g.C + r, v1);
+      grid_store(zu + (size_t)f * g.C + r, v1);
       if (want_arg) __stcs(au + (size_t)f * g.C + r, targ[r * cs + f * fs]);
     });
   }
@@ -632,17 +641,17 @@ inline bool tile_scatter_config(const ctb_shape* s, bool sum, bool want_arg, Til
   return tile_config(s, (sum || want_arg) ? 2 : 1, 0, out, (!sum || quad_sum) && s->dim == 3);
 }
 
-template <int D, bool SUM, int LAYOUT>
-cudaError_t launch_tile_scatter(const float* keys, const float* feat, const float* pad, float* z, int* arg,
+template <int D, bool SUM, int LAYOUT, typename GT>
+cudaError_t launch_tile_scatter(const float* keys, const float* feat, const float* pad, GT* z, int* arg,
                                 const ctb_shape* s, const TileConfig& c, cudaStream_t stream) {
   const Grid<D> g = make_grid<D>(s->size);
   const int groups = (s->F + c.FG - 1) / c.FG;
   const long long blocks = (long long)s->B * s->H * groups * c.slabs;
   if (blocks >= (1ll << 31)) return cudaErrorNotSupported;
-  cudaError_t e = cudaFuncSetAttribute(tile_scatter_kernel<D, SUM, LAYOUT>,
+  cudaError_t e = cudaFuncSetAttribute(tile_scatter_kernel<D, SUM, LAYOUT, GT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
-  tile_scatter_kernel<D, SUM, LAYOUT><<<(unsigned)blocks, kTileThreads, c.smem, stream>>>(
+  tile_scatter_kernel<D, SUM, LAYOUT, GT><<<(unsigned)blocks, kTileThreads, c.smem, stream>>>(
       keys, feat, pad, z, arg, g, s->H, s->F, s->N, c.FG, c.R, c.slabs, groups, c.words);
   return cudaGetLastError();
 }
@@ -653,24 +662,24 @@ inline int effective_layout(int layout, const void* p1, const void* p2) {
   return layout;
 }
 
-template <int D>
-cudaError_t tile_scatter(const float* keys, const float* feat, const float* pad, float* z, int* arg,
+template <int D, typename GT>
+cudaError_t tile_scatter(const float* keys, const float* feat, const float* pad, GT* z, int* arg,
                          const ctb_shape* s, bool sum, cudaStream_t stream) {
   TileConfig c;
   if (!tile_scatter_config(s, sum, arg != nullptr, &c)) return cudaErrorNotSupported;
   switch (effective_layout(c.layout, z, arg)) {
     case TILE_PM4:
-      return sum ? launch_tile_scatter<D, true, TILE_PM4>(keys, feat, pad, z, arg, s, c, stream)
-                 : launch_tile_scatter<D, false, TILE_PM4>(keys, feat, pad, z, arg, s, c, stream);
+      return sum ? launch_tile_scatter<D, true, TILE_PM4, GT>(keys, feat, pad, z, arg, s, c, stream)
+                 : launch_tile_scatter<D, false, TILE_PM4, GT>(keys, feat, pad, z, arg, s, c, stream);
     case TILE_PM1:
-      return sum ? launch_tile_scatter<D, true, TILE_PM1>(keys, feat, pad, z, arg, s, c, stream)
-                 : launch_tile_scatter<D, false, TILE_PM1>(keys, feat, pad, z, arg, s, c, stream);
+      return sum ? launch_tile_scatter<D, true, TILE_PM1, GT>(keys, feat, pad, z, arg, s, c, stream)
+                 : launch_tile_scatter<D, false, TILE_PM1, GT>(keys, feat, pad, z, arg, s, c, stream);
     case TILE_CLQ:
-      return sum ? launch_tile_scatter<D, true, TILE_CLQ>(keys, feat, pad, z, arg, s, c, stream)
-                 : launch_tile_scatter<D, false, TILE_CLQ>(keys, feat, pad, z, arg, s, c, stream);
+      return sum ? launch_tile_scatter<D, true, TILE_CLQ, GT>(keys, feat, pad, z, arg, s, c, stream)
+                 : launch_tile_scatter<D, false, TILE_CLQ, GT>(keys, feat, pad, z, arg, s, c, stream);
     default:
-      return sum ? launch_tile_scatter<D, true, TILE_CL>(keys, feat, pad, z, arg, s, c, stream)
-                 : launch_tile_scatter<D, false, TILE_CL>(keys, feat, pad, z, arg, s, c, stream);
+      return sum ? launch_tile_scatter<D, true, TILE_CL, GT>(keys, feat, pad, z, arg, s, c, stream)
+                 : launch_tile_scatter<D, false, TILE_CL, GT>(keys, feat, pad, z, arg, s, c, stream);
   }
 }
 
@@ -679,13 +688,14 @@ enum GatherMode { GATHER_SLICE_FWD = 0, GATHER_SLICE_BWD_KEYS = 1, GATHER_SPLAT_
 
 // One CTA = (unit, slab).  Loops over channel groups; every point is resolved in the single slab that holds
 // its base row, so grad_keys needs no cross-CTA reduction.
-template <int D, int MODE, int LAYOUT>
+template <int D, int MODE, int LAYOUT, typename GT>
 __global__ void __launch_bounds__(kTileThreads, 2)
-tile_gather_kernel(const float* __restrict__ keys, const float* __restrict__ t1, const int* __restrict__ t2,
+tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, const int* __restrict__ t2,
                    const float* __restrict__ in, const float* __restrict__ pad, float* __restrict__ out,
                    float* __restrict__ grad_keys, Grid<D> g, int H, int F, int N, int FG, int R, int slabs, int tw) {
   constexpr int S = 1 << D;
   constexpr bool CL = LAYOUT == TILE_CL || LAYOUT == TILE_CLQ;
+  constexpr bool TMA = LAYOUT == TILE_PM4 && std::is_same<GT, float>::value;   // raw tile copy by the copy engine
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int stride0 = g.stride[0];
   const int W0 = g.W[0];
@@ -708,26 +718,26 @@ tile_gather_kernel(const float* __restrict__ keys, const float* __restrict__ t1,
   const float* ku = keys + (size_t)unit * D * N;
   const float* pu = pad ? pad + (size_t)(unit / H) * N : nullptr;
 
-  if constexpr (LAYOUT == TILE_PM4) {
+  if constexpr (TMA) {
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
   }
   int cnt = N;
-  if (LAYOUT != TILE_PM4 && slabs > 1) cnt = compact_slab_points<D, false>(ku, N, g, x0, x1, sel, counter);
+  if (!TMA && slabs > 1) cnt = compact_slab_points<D, false>(ku, N, g, x0, x1, sel, counter);
 
   uint32_t parity = 0;
   for (int f0 = 0; f0 < F; f0 += FG) {
     const int fg = min(FG, F - f0);
     if (f0 > 0) __syncthreads();                 // previous group's readers are done with the tile
-    const float* g1 = t1 + ((size_t)unit * F + f0) * g.C + cell0;
+    const GT* g1 = t1 + ((size_t)unit * F + f0) * g.C + cell0;
     const int* g2 = MODE == GATHER_SPLAT_BWD ? t2 + ((size_t)unit * F + f0) * g.C + cell0 : nullptr;
-    if constexpr (LAYOUT == TILE_PM4) {
+    if constexpr (TMA) {
       // one thread hands the whole tile to the copy engine; the CTA compacts its points meanwhile
       if (threadIdx.x == 0) {
         const uint32_t plane_bytes = (uint32_t)ncell * 4u;
         mbar_expect_tx(bar, plane_bytes * fg * (MODE == GATHER_SPLAT_BWD ? 2u : 1u));
         for (int f = 0; f < fg; ++f) {
-          bulk_g2s(s1 + (size_t)f * tile_cells, g1 + (size_t)f * g.C, plane_bytes, bar);
+          bulk_g2s(s1 + (size_t)f * tile_cells, (const float*)g1 + (size_t)f * g.C, plane_bytes, bar);
           if constexpr (MODE == GATHER_SPLAT_BWD)
             bulk_g2s(s2 + (size_t)f * tile_cells, g2 + (size_t)f * g.C, plane_bytes, bar);
         }
@@ -737,7 +747,7 @@ tile_gather_kernel(const float* __restrict__ keys, const float* __restrict__ t1,
       parity ^= 1u;
     } else {
       for_each_plane_element(fg, ncell, [&](int f, int r) {
-        s1[r * cs + f * fs] = __ldcs(g1 + (size_t)f * g.C + r);
+        s1[r * cs + f * fs] = grid_load(g1 + (size_t)f * g.C + r);
         if constexpr (MODE == GATHER_SPLAT_BWD) s2[r * cs + f * fs] = __ldcs(g2 + (size_t)f * g.C + r);
       });
       __syncthreads();
@@ -916,30 +926,30 @@ inline bool gather_config(const ctb_shape* s, int mode, TileConfig* out) {
   return tile_config(s, mode == GATHER_SPLAT_BWD ? 2 : 1, 1, out, mode == GATHER_SLICE_FWD && s->dim == 3);
 }
 
-template <int D, int MODE, int LAYOUT>
-cudaError_t launch_gather(const float* keys, const float* t1, const int* t2, const float* in, const float* pad,
+template <int D, int MODE, int LAYOUT, typename GT>
+cudaError_t launch_gather(const float* keys, const GT* t1, const int* t2, const float* in, const float* pad,
                           float* out, float* grad_keys, const ctb_shape* s, const TileConfig& c, cudaStream_t stream) {
   const Grid<D> g = make_grid<D>(s->size);
   const long long blocks = (long long)s->B * s->H * c.slabs;
   if (blocks >= (1ll << 31)) return cudaErrorNotSupported;
-  cudaError_t e = cudaFuncSetAttribute(tile_gather_kernel<D, MODE, LAYOUT>,
+  cudaError_t e = cudaFuncSetAttribute(tile_gather_kernel<D, MODE, LAYOUT, GT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
-  tile_gather_kernel<D, MODE, LAYOUT><<<(unsigned)blocks, kTileThreads, c.smem, stream>>>(
+  tile_gather_kernel<D, MODE, LAYOUT, GT><<<(unsigned)blocks, kTileThreads, c.smem, stream>>>(
       keys, t1, t2, in, pad, out, grad_keys, g, s->H, s->F, s->N, c.FG, c.R, c.slabs, c.words);
   return cudaGetLastError();
 }
 
-template <int D, int MODE>
-cudaError_t tile_gather(const float* keys, const float* t1, const int* t2, const float* in, const float* pad,
+template <int D, int MODE, typename GT>
+cudaError_t tile_gather(const float* keys, const GT* t1, const int* t2, const float* in, const float* pad,
                         float* out, float* grad_keys, const ctb_shape* s, cudaStream_t stream) {
   TileConfig c;
   if (!gather_config(s, MODE, &c)) return cudaErrorNotSupported;
   switch (effective_layout(c.layout, t1, t2)) {
-    case TILE_PM4: return launch_gather<D, MODE, TILE_PM4>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
-    case TILE_PM1: return launch_gather<D, MODE, TILE_PM1>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
-    case TILE_CLQ: return launch_gather<D, MODE, TILE_CLQ>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
-    default: return launch_gather<D, MODE, TILE_CL>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
+    case TILE_PM4: return launch_gather<D, MODE, TILE_PM4, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
+    case TILE_PM1: return launch_gather<D, MODE, TILE_PM1, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
+    case TILE_CLQ: return launch_gather<D, MODE, TILE_CLQ, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
+    default: return launch_gather<D, MODE, TILE_CL, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
   }
 }
 

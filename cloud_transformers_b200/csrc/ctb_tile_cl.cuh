@@ -23,10 +23,10 @@ inline size_t cl_extra_bytes(int FG, int dim) {
   return (size_t)cl_stage_words(FG) * 4 + (size_t)kClChunk * (1 << dim) * 8 + 16;
 }
 
-template <int D, bool SUM>
+template <int D, bool SUM, typename GT>
 __global__ void __launch_bounds__(kTileThreads, 2)
 cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat, const float* __restrict__ pad,
-                  float* __restrict__ z, int* __restrict__ arg, Grid<D> g, int H, int F, int N, int FG, int groups,
+                  GT* __restrict__ z, int* __restrict__ arg, Grid<D> g, int H, int F, int N, int FG, int groups,
                   int tw, int LP) {
   constexpr int S = 1 << D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -183,7 +183,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
     }
   }
 
-  float* zu = z + ((size_t)unit * F + f0) * g.C;
+  GT* zu = z + ((size_t)unit * F + f0) * g.C;
   int* au = want_arg ? arg + ((size_t)unit * F + f0) * g.C : nullptr;
   for_each_plane_element(fg, g.C, [&](int f, int r) {
     float v1 = tval[r * fgp + f];
@@ -193,14 +193,14 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
       const long long q = limb_bits > 0 ? ((long long)hi << limb_bits) + lo : (((long long)hi << 32) | lo);
       v1 = __ll2float_rn(q) * inv_scale;
     }
-    __stcs(zu + (size_t)f * g.C + r, v1);
+    grid_store(zu + (size_t)f * g.C + r, v1);
     if (want_arg) __stcs(au + (size_t)f * g.C + r, targ[r * fgp + f]);
   });
 }
 
 // host: use the channel-lane kernel when the shape is channel-last, fits whole, and a group has <= 32 channels
-template <int D>
-bool cl_scatter_try(const float* keys, const float* feat, const float* pad, float* z, int* arg, const ctb_shape* s,
+template <int D, typename GT>
+bool cl_scatter_try(const float* keys, const float* feat, const float* pad, GT* z, int* arg, const ctb_shape* s,
                     bool sum, cudaStream_t stream, cudaError_t* err) {
   TileConfig c;
   if (!tile_scatter_config(s, sum, arg != nullptr, &c)) return false;
@@ -223,14 +223,14 @@ bool cl_scatter_try(const float* keys, const float* feat, const float* pad, floa
   const long long blocks = (long long)s->B * s->H * groups;
   if (blocks >= (1ll << 31)) return false;
   if (sum) {
-    *err = cudaFuncSetAttribute(cl_scatter_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    *err = cudaFuncSetAttribute(cl_scatter_kernel<D, true, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (*err != cudaSuccess) return true;
-    cl_scatter_kernel<D, true><<<(unsigned)blocks, kTileThreads, smem, stream>>>(keys, feat, pad, z, arg, g, s->H, s->F,
+    cl_scatter_kernel<D, true, GT><<<(unsigned)blocks, kTileThreads, smem, stream>>>(keys, feat, pad, z, arg, g, s->H, s->F,
                                                                                s->N, FG, groups, tw, LP);
   } else {
-    *err = cudaFuncSetAttribute(cl_scatter_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    *err = cudaFuncSetAttribute(cl_scatter_kernel<D, false, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (*err != cudaSuccess) return true;
-    cl_scatter_kernel<D, false><<<(unsigned)blocks, kTileThreads, smem, stream>>>(keys, feat, pad, z, arg, g, s->H, s->F,
+    cl_scatter_kernel<D, false, GT><<<(unsigned)blocks, kTileThreads, smem, stream>>>(keys, feat, pad, z, arg, g, s->H, s->F,
                                                                                 s->N, FG, groups, tw, LP);
   }
   *err = cudaGetLastError();

@@ -70,8 +70,8 @@ class Geometry:
             c *= s
         self.C = c
 
-    def shape(self, B, F, N):
-        return _lib.make_shape(B, self.heads, F, N, self.dim, self.sizes)
+    def shape(self, B, F, N, grid_dtype=0):
+        return _lib.make_shape(B, self.heads, F, N, self.dim, self.sizes, grid_dtype)
 
 
 def _call(name, *args):
@@ -239,9 +239,18 @@ class PositionsHandle:
         return self._plan
 
 
+def _grid_dtype_code(dtype, mode):
+    """bf16 grids are handled natively by the TILE kernels; everything else goes through fp32."""
+    return _lib.DTYPE_BF16 if (dtype == torch.bfloat16 and mode == _lib.MODE_TILE) else _lib.DTYPE_F32
+
+
+def _grid_c(t, code):
+    return t.contiguous() if code == _lib.DTYPE_BF16 else _f32c(t)
+
+
 class _FusedSplatFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, keys, features, pad, handle, reduce):
+    def forward(ctx, keys, features, pad, handle, reduce, out_dtype=None):
         _require_cuda(keys, features, pad)
         geom = handle.geom
         k, f_c, p_c = handle.keys_c(), _f32c(features), _f32c(pad)
@@ -249,14 +258,19 @@ class _FusedSplatFn(torch.autograd.Function):
         F = f_c.size(1) // geom.heads
         mode = handle.mode_for(_lib.OP_SPLAT_FWD, F, reduce)
         plan = handle.plan() if mode == _lib.MODE_DETERMINISTIC else None
-        z = torch.empty((B, geom.heads * F) + geom.sizes, dtype=torch.float32, device=f_c.device)
+        gd = _grid_dtype_code(out_dtype, mode)
+        ctx.gd = gd
+        z = torch.empty((B, geom.heads * F) + geom.sizes,
+                        dtype=torch.bfloat16 if gd == _lib.DTYPE_BF16 else torch.float32, device=f_c.device)
         arg = torch.empty((B, geom.heads * F, geom.C), dtype=torch.int32, device=f_c.device) \
             if reduce == _lib.REDUCE_MAX else None
         with torch.cuda.device(f_c.device):
             _call("ctb_splat_fwd_keys", _ptr(k), _ptr(f_c), _ptr(p_c), _ptr(z), _ptr(arg),
-                  ctypes.byref(geom.shape(B, F, N)), reduce, mode, _ptr(plan), _stream(f_c))
+                  ctypes.byref(geom.shape(B, F, N, gd)), reduce, mode, _ptr(plan), _stream(f_c))
         ctx.save_for_backward(k, f_c, p_c, arg)
         ctx.handle, ctx.reduce = handle, reduce
+        if out_dtype is not None and z.dtype != out_dtype:
+            z = z.to(out_dtype)
         return z
 
     @staticmethod
@@ -268,13 +282,14 @@ class _FusedSplatFn(torch.autograd.Function):
         B, N = f_c.size(0), f_c.size(-1)
         F = f_c.size(1) // geom.heads
         mode = handle.mode_for(_lib.OP_SPLAT_BWD, F, ctx.reduce)
-        gz_c = _f32c(gz)
+        gd = _grid_dtype_code(gz.dtype, mode)
+        gz_c = _grid_c(gz, gd)
         gf = torch.empty_like(f_c)
         gk = torch.empty_like(k)
         with torch.cuda.device(f_c.device):
             _call("ctb_splat_bwd_keys", _ptr(k), _ptr(f_c), _ptr(p_c), _ptr(gz_c), _ptr(arg), _ptr(gf), _ptr(gk),
-                  ctypes.byref(geom.shape(B, F, N)), ctx.reduce, mode, _stream(f_c))
-        return gk, gf, None, None, None
+                  ctypes.byref(geom.shape(B, F, N, gd)), ctx.reduce, mode, _stream(f_c))
+        return gk, gf, None, None, None, None
 
 
 class _FusedSliceFn(torch.autograd.Function):
@@ -282,13 +297,15 @@ class _FusedSliceFn(torch.autograd.Function):
     def forward(ctx, keys, grid, pad, handle):
         _require_cuda(keys, grid, pad)
         geom = handle.geom
-        k, g_c, p_c = handle.keys_c(), _f32c(grid), _f32c(pad)
+        k, p_c = handle.keys_c(), _f32c(pad)
         B, N = k.size(0), k.size(-1)
-        F = g_c.size(1) // geom.heads
+        F = grid.size(1) // geom.heads
         mode = handle.mode_for(_lib.OP_SLICE_FWD, F)
+        gd = _grid_dtype_code(grid.dtype, mode)
+        g_c = _grid_c(grid, gd)
         out = torch.empty((B, geom.heads * F, N), dtype=torch.float32, device=g_c.device)
         with torch.cuda.device(g_c.device):
-            _call("ctb_slice_fwd_keys", _ptr(k), _ptr(g_c), _ptr(p_c), _ptr(out), ctypes.byref(geom.shape(B, F, N)),
+            _call("ctb_slice_fwd_keys", _ptr(k), _ptr(g_c), _ptr(p_c), _ptr(out), ctypes.byref(geom.shape(B, F, N, gd)),
                   mode, _stream(g_c))
         ctx.save_for_backward(k, g_c, p_c)
         ctx.handle = handle
@@ -305,17 +322,21 @@ class _FusedSliceFn(torch.autograd.Function):
         F = g_c.size(1) // geom.heads
         mode = handle.mode_for(_lib.OP_SLICE_BWD, F)
         plan = handle.plan() if mode == _lib.MODE_DETERMINISTIC else None
+        gd = _lib.DTYPE_BF16 if (g_c.dtype == torch.bfloat16 and mode == _lib.MODE_TILE) else _lib.DTYPE_F32
+        if gd == _lib.DTYPE_F32 and g_c.dtype != torch.float32:
+            g_c = g_c.float()
         go_c = _f32c(go)
         gg = torch.empty_like(g_c)
         gk = torch.empty_like(k)
         with torch.cuda.device(g_c.device):
             _call("ctb_slice_bwd_keys", _ptr(k), _ptr(g_c), _ptr(p_c), _ptr(go_c), _ptr(gg), _ptr(gk),
-                  ctypes.byref(geom.shape(B, F, N)), mode, _ptr(plan), _stream(g_c))
+                  ctypes.byref(geom.shape(B, F, N, gd)), mode, _ptr(plan), _stream(g_c))
         return gk, gg.to(ctx.grid_dtype), None, None
 
 
-def fused_splat(handle, features, pad=None, reduce=_lib.REDUCE_MAX):
-    return _FusedSplatFn.apply(handle.keys, features, pad, handle, reduce)
+def fused_splat(handle, features, pad=None, reduce=_lib.REDUCE_MAX, out_dtype=None):
+    """out_dtype=torch.bfloat16 selects the bf16 grid storage mode (fp32 arithmetic, bf16 z)."""
+    return _FusedSplatFn.apply(handle.keys, features, pad, handle, reduce, out_dtype)
 
 
 def fused_slice(handle, grid, pad=None):

@@ -18,13 +18,16 @@ from .functional import Geometry, _call, _ptr, _stream
 
 
 class HotPath:
-    def __init__(self, tensor_size, heads, dim, B, F, N, device, mode="auto", reduce="max"):
+    def __init__(self, tensor_size, heads, dim, B, F, N, device, mode="auto", reduce="max", grid_dtype=torch.float32):
         sizes = [tensor_size] * dim if isinstance(tensor_size, int) else list(tensor_size)
         self.geom = Geometry(sizes, heads, dim)
         self.B, self.F, self.N = B, F, N
         self.device = torch.device(device)
         self.reduce = _lib.REDUCE_MAX if reduce == "max" else _lib.REDUCE_SUM
-        self.shape = self.geom.shape(B, F, N)
+        self.grid_dtype = grid_dtype
+        if grid_dtype == torch.bfloat16 and mode not in ("auto", "tile"):
+            raise ValueError("bf16 grid storage needs the tile kernels")
+        self.shape = self.geom.shape(B, F, N, _lib.DTYPE_BF16 if grid_dtype == torch.bfloat16 else _lib.DTYPE_F32)
         lib = _lib.load()
         want = {"auto": _lib.MODE_TILE, "tile": _lib.MODE_TILE, "deterministic": _lib.MODE_DETERMINISTIC,
                 "atomic": _lib.MODE_ATOMIC}[mode]
@@ -34,10 +37,12 @@ class HotPath:
         self.modes = [want if s else _lib.MODE_ATOMIC for s in sup]
         H, C = heads, self.geom.C
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.z = torch.empty((B, H * F) + self.geom.sizes, **f32)
+        if grid_dtype == torch.bfloat16 and not all(sup):
+            raise _lib.CtbError("ctb_mode_supported", _lib.CTB_ERR_UNSUPPORTED, "bf16 grids need a tile-supported shape")
+        self.z = torch.empty((B, H * F) + self.geom.sizes, dtype=grid_dtype, device=self.device)
         self.arg = torch.empty((B, H * F, C), dtype=torch.int32, device=self.device)
         self.out = torch.empty((B, H * F, N), **f32)
-        self.grad_grid = torch.empty((B, H * F) + self.geom.sizes, **f32)
+        self.grad_grid = torch.empty((B, H * F) + self.geom.sizes, dtype=grid_dtype, device=self.device)
         self.grad_keys_slice = torch.empty((B, H * dim, N), **f32)
         self.grad_keys_splat = torch.empty((B, H * dim, N), **f32)
         self.grad_feat = torch.empty((B, H * F, N), **f32)
@@ -93,15 +98,17 @@ class HotPath:
         self.splat_bwd(keys, feat, grad_z, pad)
 
 
-def algorithmic_bytes(N, dim, F, C, e=4):
-    """minimal HBM bytes per (batch, head) unit, per pass and in total (reduce = max)."""
+def algorithmic_bytes(N, dim, F, C, e=4, e_grid=None):
+    """minimal HBM bytes per (batch, head) unit, per pass and in total (reduce = max).
+    e = bytes per feature element, e_grid = bytes per grid element (bf16 grid storage mode: 2)."""
     d = dim
+    eg = e if e_grid is None else e_grid
     per = {
-        "splat_fwd": N * (4 * d + e * F) + e * F * C,
-        "slice_fwd": N * (4 * d + e * F) + e * F * C,
-        "slice_bwd": N * (8 * d + e * F) + 2 * e * F * C,
-        "splat_bwd": N * (8 * d + 2 * e * F) + 2 * e * F * C,
+        "splat_fwd": N * (4 * d + e * F) + eg * F * C,
+        "slice_fwd": N * (4 * d + e * F) + eg * F * C,
+        "slice_bwd": N * (8 * d + e * F) + 2 * eg * F * C,
+        "splat_bwd": N * (8 * d + 2 * e * F) + 2 * eg * F * C,
     }
     per["total"] = sum(per.values())
-    assert per["total"] == N * (24 * d + 5 * e * F) + 6 * e * F * C
+    assert per["total"] == N * (24 * d + 5 * e * F) + 6 * eg * F * C
     return per

@@ -60,6 +60,11 @@ typedef enum ctb_reduce { CTB_REDUCE_MAX = 0, CTB_REDUCE_SUM = 1 } ctb_reduce;
  *                 plain stores -- no atomics anywhere, bit-identical from run to run. */
 typedef enum ctb_mode { CTB_MODE_ATOMIC = 0, CTB_MODE_DETERMINISTIC = 1, CTB_MODE_TILE = 2 } ctb_mode;
 
+/* element type of the GRID tensors (z, convolved grid, grad_grid, grad_z) of the fused entries.  BF16 is the storage
+ * mode of the north star: grids live in HBM as bf16, every product / max / sum is still computed in fp32 on chip
+ * (tolerance rel 1e-2 instead of 1e-5).  Keys, features, per-point outputs and arg are unaffected. */
+typedef enum ctb_dtype { CTB_DTYPE_F32 = 0, CTB_DTYPE_BF16 = 1 } ctb_dtype;
+
 /* geometry of one call.  size[2] is ignored when dim == 2. */
 typedef struct ctb_shape {
   int32_t B;       /* batch of clouds */
@@ -68,6 +73,7 @@ typedef struct ctb_shape {
   int32_t N;       /* points per cloud */
   int32_t dim;     /* 2 or 3 */
   int32_t size[3]; /* grid extent per axis, each >= 2 (tensor_size, cloud_transform.py:41-46) */
+  int32_t grid_dtype; /* ctb_dtype of the grid tensors; BF16 only with CTB_MODE_TILE fused entries */
 } ctb_shape;
 
 int ctb_version(void);
@@ -123,15 +129,16 @@ size_t ctb_plan_bytes(const ctb_shape* shape);
 /* sort the S*N (point, corner) entries of every (b, h) unit by destination cell. */
 int ctb_plan_build(const float* keys, void* plan, size_t plan_bytes, const ctb_shape* shape, void* stream);
 
-int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pad, float* z, int32_t* arg,
+/* grid tensors (z, grad_z, grid, grad_grid) are void*: f32 or bf16 according to shape->grid_dtype */
+int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pad, void* z, int32_t* arg,
                        const ctb_shape* shape, int reduce, int mode, const void* plan, void* stream);
-int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pad, const float* grad_z,
+int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pad, const void* grad_z,
                        const int32_t* arg, float* grad_features, float* grad_keys, const ctb_shape* shape,
                        int reduce, int mode, void* stream);
-int ctb_slice_fwd_keys(const float* keys, const float* grid, const float* pad, float* out,
+int ctb_slice_fwd_keys(const float* keys, const void* grid, const float* pad, float* out,
                        const ctb_shape* shape, int mode, void* stream);
-int ctb_slice_bwd_keys(const float* keys, const float* grid, const float* pad, const float* grad_out,
-                       float* grad_grid, float* grad_keys, const ctb_shape* shape, int mode,
+int ctb_slice_bwd_keys(const float* keys, const void* grid, const float* pad, const float* grad_out,
+                       void* grad_grid, float* grad_keys, const ctb_shape* shape, int mode,
                        const void* plan, void* stream);
 
 /* ---- A8: per-head projection + tanh in front of DifferentiablePositions ------------------------------ */

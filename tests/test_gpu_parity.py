@@ -509,3 +509,43 @@ def test_large_shapes_all_algorithms_agree(shape):
     z_o = O.splat_fwd(lc_o, idx_o, fb, W, 1, dim)
     assert np.array_equal(n(zt[:1, :F]), z_o)
     assert_close(n(ot[:1, :F]), O.slice_fwd(lc_o, idx_o, np.sin(z_o * 3 + 0.1).astype(np.float32), 1), "slice")
+
+
+# --- bf16 grid storage mode (north star: rel 1e-2) -----------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 128, 4, 4, 2048, 2), (3, 32, 4, 4, 2048, 1), (2, 64, 4, 16, 2048, 1),
+                                   (3, 8, 4, 32, 2048, 1), (2, (24, 40), 3, 5, 777, 2)],
+                         ids=lambda s: "d%d_w%s_h%d_f%d_n%d_b%d" % s)
+def test_bf16_grid_storage_mode(shape):
+    """Grids (z, convolved, grad_grid, grad_z) stored as bf16, arithmetic in fp32: against the fp32 oracle fed with the
+    bf16-rounded grids, within rel 1e-2 (abs floor 1e-2 * max|ref|)."""
+    dim, W, H, F, N, B = shape
+    keys, feat, pad = make_inputs(17, B, H, dim, F, N, pad=True)
+    sizes = tuple(O._sizes(W, dim))
+    rng = np.random.default_rng(9)
+    bf = lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+    conv = bf(rng.standard_normal((B, H * F) + sizes).astype(np.float32))
+    go = rng.standard_normal((B, H * F, N)).astype(np.float32)
+    gz = bf(rng.standard_normal(conv.shape).astype(np.float32))
+    ref = oracle_block(keys, feat, pad, conv, go, gz, W, H, dim)
+    ctb.config.mode = "tile"
+    dp = ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim)
+    sp = ctb.Splat(tensor_size=W, heads=H, dim=dim, out_dtype=torch.bfloat16)
+    sl = ctb.Slice(tensor_size=W, heads=H, dim=dim)
+    k = t(keys).requires_grad_(True)
+    f = t(feat).requires_grad_(True)
+    c = t(conv).to(torch.bfloat16).requires_grad_(True)
+    lc, idx = dp(k)
+    z = sp(lc, idx, f, t(pad))
+    assert z.dtype == torch.bfloat16
+    out = sl(lc, idx, c, t(pad))
+    assert out.dtype == torch.float32
+    assert_close(n(z.float()), ref["z"], "bf16 z", rtol=1e-2, atol_scale=1e-2)
+    assert_close(n(out), ref["out"], "slice of bf16 grid", rtol=1e-2, atol_scale=1e-2)
+    (out * t(go)).sum().backward(retain_graph=True)
+    assert c.grad.dtype == torch.bfloat16
+    assert_close(n(c.grad.float()), ref["gconv"], "bf16 grad grid", rtol=1e-2, atol_scale=1e-2)
+    assert_close(n(k.grad), ref["gk_slice"], "grad keys via slice", rtol=1e-2, atol_scale=1e-2)
+    k.grad = None
+    (z.float() * t(gz)).sum().backward()
+    assert_close(n(f.grad), ref["gfeat"], "grad features", rtol=1e-2, atol_scale=1e-2)
+    assert_close(n(k.grad), ref["gk_splat"], "grad keys via splat", rtol=1e-2, atol_scale=1e-2)
