@@ -363,6 +363,7 @@ def run_train(args, dev, world, rank):
     from cloud_transformers_b200.mhct import ScanObjectTrunk
     try:
         torch.manual_seed(1234 + rank)
+        torch.backends.cudnn.benchmark = True          # as train_classification.py:58
         B = args.train_batch
         model = ScanObjectTrunk().to(dev)
         if world > 1:

@@ -441,23 +441,35 @@ int ctb_project_fwd(const float* pcd, const float* keys_res, float res_scale, co
 
 int ctb_project_bwd(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
                     const float* scales, const float* keys, const float* grad_keys, float* grad_pcd,
-                    float* grad_keys_res, float* param_acc, const ctb_shape* shape, void* stream) {
+                    float* grad_keys_res, float* param_acc, float* workspace, size_t workspace_bytes,
+                    const ctb_shape* shape, void* stream) {
   int st = check_shape(shape, false);
   if (st) return st;
   if (!pcd || !shift || !rot || !keys || !grad_keys || !grad_pcd || !param_acc) return CTB_ERR_INVALID_ARGUMENT;
   if (keys_res && !grad_keys_res) return CTB_ERR_INVALID_ARGUMENT;
-  const int chunks = (shape->N + ctb::kProjBlock - 1) / ctb::kProjBlock;
+  if (!workspace || workspace_bytes < ctb_project_bwd_workspace_bytes(shape)) return CTB_ERR_WORKSPACE;
+  const int chunks = (shape->N + 31) / 32;
   const unsigned blocks = (unsigned)((long long)shape->B * chunks);
+  const dim3 block(32, shape->H < 32 ? shape->H : 32);
   if (shape->dim == 2)
-    ctb::project_bwd_kernel<2><<<blocks, ctb::kProjBlock, 0, (cudaStream_t)stream>>>(
-        pcd, keys_res, res_scale, shift, rot, scales, keys, grad_keys, grad_pcd, grad_keys_res, param_acc, shape->H,
+    ctb::project_bwd_kernel<2><<<blocks, block, 0, (cudaStream_t)stream>>>(
+        pcd, keys_res, res_scale, shift, rot, scales, keys, grad_keys, grad_pcd, grad_keys_res, workspace, shape->H,
         shape->N, chunks);
   else
-    ctb::project_bwd_kernel<3><<<blocks, ctb::kProjBlock, 0, (cudaStream_t)stream>>>(
-        pcd, keys_res, res_scale, shift, rot, scales, keys, grad_keys, grad_pcd, grad_keys_res, param_acc, shape->H,
+    ctb::project_bwd_kernel<3><<<blocks, block, 0, (cudaStream_t)stream>>>(
+        pcd, keys_res, res_scale, shift, rot, scales, keys, grad_keys, grad_pcd, grad_keys_res, workspace, shape->H,
         shape->N, chunks);
   CTB_LAUNCH_CHECK();
+  const int cells = shape->H * ctb::kProjAcc;
+  ctb::project_param_reduce_kernel<<<cells, 128, 0, (cudaStream_t)stream>>>(workspace, param_acc, (int)blocks, shape->H);
+  CTB_LAUNCH_CHECK();
   return CTB_OK;
+}
+
+size_t ctb_project_bwd_workspace_bytes(const ctb_shape* shape) {
+  if (check_shape(shape, false)) return 0;
+  const size_t chunks = (size_t)(shape->N + 31) / 32;
+  return (size_t)shape->B * chunks * shape->H * ctb::kProjAcc * sizeof(float);
 }
 
 int ctb_count_occupied(const float* z, uint64_t n_elements, unsigned long long* count, void* stream) {

@@ -43,35 +43,40 @@ project_fwd_kernel(const float* __restrict__ pcd, const float* __restrict__ res,
   }
 }
 
-// One thread per (b, n), loop over heads.  acc is [H][kProjAcc] floats, zeroed by the caller.
+// Backward.  CTA = 32 consecutive points x up to 32 heads (one warp per head): the per-head parameter gradients are
+// warp-reduced over the 32 points and written as per-CTA partials (summed in a fixed order by
+// project_param_reduce_kernel), grad_pcd is summed over the heads through shared memory in a fixed order --
+// everything is deterministic.  partial is [chunks * B][H][kProjAcc].
 template <int D>
-__global__ void __launch_bounds__(kProjBlock)
+__global__ void __launch_bounds__(1024)
 project_bwd_kernel(const float* __restrict__ pcd, const float* __restrict__ res, float res_scale,
                    const float* __restrict__ shift, const float* __restrict__ rot, const float* __restrict__ scales,
                    const float* __restrict__ keys, const float* __restrict__ grad_keys,
-                   float* __restrict__ grad_pcd, float* __restrict__ grad_res, float* __restrict__ acc, int H, int N,
+                   float* __restrict__ grad_pcd, float* __restrict__ grad_res, float* __restrict__ partial, int H, int N,
                    int chunks) {
+  __shared__ float gp_s[32][3][33];
   const int b = blockIdx.x / chunks;
-  const int n = (blockIdx.x % chunks) * kProjBlock + threadIdx.x;
+  const int n = (blockIdx.x % chunks) * 32 + threadIdx.x;
   const bool live = n < N;
-  const int lane = threadIdx.x & 31;
-  float pc[3] = {0.f, 0.f, 0.f}, gpcd[3] = {0.f, 0.f, 0.f};
+  const int hw = threadIdx.y;                 // warp index = head slot
+  float pc[3] = {0.f, 0.f, 0.f}, gsum[3] = {0.f, 0.f, 0.f};
   if (live)
 #pragma unroll
     for (int c = 0; c < 3; ++c) pc[c] = __ldg(pcd + ((size_t)b * 3 + c) * N + n);
-  for (int h = 0; h < H; ++h) {
-    const size_t unit = (size_t)b * H + h;
+  for (int h0 = 0; h0 < H; h0 += blockDim.y) {
+    const int h = h0 + hw;
     float v[kProjAcc];
 #pragma unroll
     for (int i = 0; i < kProjAcc; ++i) v[i] = 0.0f;
-    if (live) {
+    float gp[3] = {0.f, 0.f, 0.f};
+    if (live && h < H) {
+      const size_t unit = (size_t)b * H + h;
       float p[3], r[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         if (res) r[c] = __ldg(res + (unit * 3 + c) * N + n);
         p[c] = pc[c] + res_scale * r[c] + __ldg(shift + h * 3 + c);
       }
-      float gp[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         const float t = __ldg(keys + (unit * D + j) * N + n);
@@ -92,21 +97,44 @@ project_bwd_kernel(const float* __restrict__ pcd, const float* __restrict__ res,
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         v[c] = gp[c];                                // d / d shift[h][c]
-        gpcd[c] += gp[c];
         if (grad_res) grad_res[(unit * 3 + c) * N + n] = res_scale * gp[c];
         v[15] = fmaf(gp[c], r[c], v[15]);            // d / d res_scale
       }
     }
+    // parameter gradients: reduce over the 32 points of this warp, one partial row per (CTA, head)
 #pragma unroll
     for (int i = 0; i < kProjAcc; ++i) {
       float x = v[i];
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-      if (lane == 0 && x != 0.0f) atomicAdd(acc + h * kProjAcc + i, x);
+      if (threadIdx.x == 0 && h < H) partial[((size_t)blockIdx.x * H + h) * kProjAcc + i] = x;
     }
-  }
-  if (live)
+    // grad_pcd: sum over heads in a fixed order through shared memory
+    __syncthreads();
 #pragma unroll
-    for (int c = 0; c < 3; ++c) grad_pcd[((size_t)b * 3 + c) * N + n] = gpcd[c];
+    for (int c = 0; c < 3; ++c) gp_s[hw][c][threadIdx.x] = gp[c];
+    __syncthreads();
+    if (hw == 0)
+      for (int w = 0; w < (int)blockDim.y; ++w)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gsum[c] += gp_s[w][c][threadIdx.x];
+  }
+  if (hw == 0 && live)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) grad_pcd[((size_t)b * 3 + c) * N + n] = gsum[c];
+}
+
+// acc[h][i] += sum over CTAs of partial[cta][h][i]: one 128-thread block per (h, i), fixed reduction tree
+__global__ void __launch_bounds__(128)
+project_param_reduce_kernel(const float* __restrict__ partial, float* __restrict__ acc, int ctas, int H) {
+  __shared__ float ws[4];
+  const int t = blockIdx.x;
+  const int stride = H * kProjAcc;
+  float s = 0.0f;
+  for (int c = threadIdx.x; c < ctas; c += 128) s += partial[(size_t)c * stride + t];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) acc[t] += (ws[0] + ws[1]) + (ws[2] + ws[3]);
 }
 
 }  // namespace ctb

@@ -384,10 +384,12 @@ class _ProjectFn(torch.autograd.Function):
         g_res = torch.empty_like(res_c) if res_c is not None else None
         acc = torch.zeros((heads, 16), dtype=torch.float32, device=pcd_c.device)
         sh = _lib.make_shape(B, heads, 1, N, dim, (2,) * dim)
+        ws_bytes = _lib.load().ctb_project_bwd_workspace_bytes(ctypes.byref(sh))
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=pcd_c.device)
         with torch.cuda.device(pcd_c.device):
             _call("ctb_project_bwd", _ptr(pcd_c), _ptr(res_c), ctypes.c_float(ctx.rs), _ptr(shift_c), _ptr(rot_c),
-                  _ptr(scales_c), _ptr(keys), _ptr(g), _ptr(g_pcd), _ptr(g_res), _ptr(acc), ctypes.byref(sh),
-                  _stream(pcd_c))
+                  _ptr(scales_c), _ptr(keys), _ptr(g), _ptr(g_pcd), _ptr(g_res), _ptr(acc), _ptr(ws),
+                  ctypes.c_size_t(ws_bytes), ctypes.byref(sh), _stream(pcd_c))
         g_shift = acc[:, 0:3].contiguous()
         g_rot = acc[:, 3:12].reshape(heads, 3, 3)
         g_scales = acc[:, 12:12 + dim].contiguous() if scales_c is not None else None

@@ -154,7 +154,11 @@ int ctb_project_fwd(const float* pcd, const float* keys_res, float res_scale, co
  * are written), 12-14 d scales, 15 d res_scale (per head; sum over heads for the scalar). */
 int ctb_project_bwd(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
                     const float* scales, const float* keys, const float* grad_keys, float* grad_pcd,
-                    float* grad_keys_res, float* param_acc, const ctb_shape* shape, void* stream);
+                    float* grad_keys_res, float* param_acc, float* workspace, size_t workspace_bytes,
+                    const ctb_shape* shape, void* stream);
+/* bytes of the caller-provided scratch of ctb_project_bwd (per-CTA partial parameter gradients, reduced in a
+ * fixed order so the result is deterministic). */
+size_t ctb_project_bwd_workspace_bytes(const ctb_shape* shape);
 
 /* A9  occupancy statistic of MultiHead blocks (layers/multihead_ct.py:104-105): count of |z| > 1e-9
  * accumulated into *count (u64, device memory, caller zeroes it). */
