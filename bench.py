@@ -247,7 +247,8 @@ def run_ours(args):
             "frac_of_hbm_peak": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
             "roofline": {"bound": "hbm", "kernel": "%s/%s" % (top["op"], top["class"]), "achieved": top["gbs"],
                          "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": round(top["gbs"] / peak, 4),
-                         "traffic": None, "share_of_step": round(top["ms"] / total_op_ms, 4)},
+                         "traffic": ncu_traffic(top["op"], top["class"]), "algorithmic_bytes": top["bytes"],
+                         "share_of_step": round(top["ms"] / total_op_ms, 4)},
             "ops": ops,
             "e2e": e2e,
             "train": train,
@@ -259,6 +260,30 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(op, cls):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel(s) of one op, per launch, from the committed
+    `ncu --set full` capture of tools/profile_ops.py (profiles/r01_ncu_full_summary.csv: 5 kernels per class in the order
+    Splat fwd | Slice fwd | Slice bwd scatter, Slice bwd gather | Splat bwd; classes in CLASSES order)."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        ir = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum")][0]
+        iw = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum")][0]
+        unit_r, unit_w = hdr[ir], hdr[iw]
+        scale = lambda u: 1e9 if "Gbyte" in u else (1e6 if "Mbyte" in u else (1e3 if "Kbyte" in u else 1.0))
+        ci = [c[0] for c in CLASSES].index(cls)
+        pick = {"splat_fwd": [0], "slice_fwd": [1], "slice_bwd": [2, 3], "splat_bwd": [4]}[op]
+        body = rows[1:]
+        if len(body) < 5 * len(CLASSES):
+            return None
+        return int(sum(float(body[ci * 5 + k][ir]) * scale(unit_r) + float(body[ci * 5 + k][iw]) * scale(unit_w)
+                       for k in pick))
+    except Exception:
+        return None
 
 
 _FLUSH = {}
