@@ -168,7 +168,8 @@ cudaError_t tile_scatter_any(const float* keys, const float* feat, const float* 
   cudaError_t e = cudaSuccess;
   // measured (profiles/r01_*): lanes = channels wins for the contended float-sum atomics (c3d 0.52 -> 0.32 ms) but
   // not for max, whose second pass is broadcast-friendly shared loads
-  if (!no_cl && sum && ctb::cl_scatter_try<D, GT>(keys, feat, pad, z, arg, s, sum, stream, &e)) return e;
+  static const bool cl_max = getenv("CTB_CHANNEL_LANE_MAX") != nullptr;
+  if (!no_cl && (sum || cl_max) && ctb::cl_scatter_try<D, GT>(keys, feat, pad, z, arg, s, sum, stream, &e)) return e;
   return ctb::tile_scatter<D, GT>(keys, feat, pad, z, arg, s, sum, stream);
 }
 

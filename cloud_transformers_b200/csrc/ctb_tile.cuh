@@ -96,6 +96,53 @@ struct TileConfig {
 
 // channel-last pitch in words: CL odd (conflict-free scalar plane moves); CLQ = FG + 4, a multiple of 4 that is not a
 // power of two, so that the 4-channel "quads" of a cell are 16-byte aligned
+// ---- exact, order-independent sums: two carry-free 32-bit limbs ---------------------------------------
+// A contribution v is taken as the integer q = rint(v * 2^k), |q| < 2^40, and stored as q = hi * 2^20 + lo with
+// hi = rint(q / 2^20) (|hi| < 2^20) and lo = q - hi * 2^20 (|lo| <= 2^19).  A point meets a cell at most once, so with
+// at most 2048 points per work item neither limb sum can leave int32: integer adds commute, the result does not
+// depend on the order of the atomics.  The split is done on the FMA pipe with the 1.5 * 2^23 rounding constant
+// (float -> int64 conversions run on the quarter-rate XU pipe and were the top cost of the sum kernels, ncu r01).
+constexpr int kLimbBits = 20;
+constexpr int kLimbMaxCountBits = 11;       // <= 2048 contributions per cell
+constexpr float kRoundMagic = 12582912.0f;  // 1.5 * 2^23
+constexpr int kRoundMagicBits = 0x4B400000;
+
+__device__ __forceinline__ void fixed_split(float t, int& lo, int& hi) {
+  const float u = __fmaf_rn(t, 0x1p-20f, kRoundMagic);      // magic + rint(t / 2^20), one rounding
+  const float hf = __fsub_rn(u, kRoundMagic);
+  const float rem = __fmaf_rn(-hf, 0x1p20f, t);             // exact
+  const float r = __fadd_rn(rem, kRoundMagic);              // magic + rint(rem)
+  hi = __float_as_int(u) - kRoundMagicBits;
+  lo = __float_as_int(r) - kRoundMagicBits;
+}
+// Two contributions at once with the packed fp32 instructions of sm_100 (FMUL2 / FFMA2 / FADD2): same IEEE
+// roundings per element as fixed_split, half the issue slots.  t0 = x * w0, t1 = x * w1.
+__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void fixed_split2(float x, float w0, float w1, int& lo0, int& hi0, int& lo1, int& hi1) {
+  const unsigned long long xx = pack_f32x2(x, x), ww = pack_f32x2(w0, w1);
+  const unsigned long long magic = pack_f32x2(kRoundMagic, kRoundMagic), nmagic = pack_f32x2(-kRoundMagic, -kRoundMagic);
+  const unsigned long long dn = pack_f32x2(0x1p-20f, 0x1p-20f), nup = pack_f32x2(-0x1p20f, -0x1p20f);
+  unsigned long long t, u, hf, rem, r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(xx), "l"(ww));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(u) : "l"(t), "l"(dn), "l"(magic));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(hf) : "l"(u), "l"(nmagic));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rem) : "l"(hf), "l"(nup), "l"(t));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(rem), "l"(magic));
+  hi0 = (int)(unsigned)(u & 0xffffffffull) - kRoundMagicBits;
+  hi1 = (int)(unsigned)(u >> 32) - kRoundMagicBits;
+  lo0 = (int)(unsigned)(r & 0xffffffffull) - kRoundMagicBits;
+  lo1 = (int)(unsigned)(r >> 32) - kRoundMagicBits;
+}
+// scale exponent for the two-limb format: max|v| * 2^k <= 2^40 / 1.001, so that |hi| stays below 2^20
+__device__ __forceinline__ int fixed_split_exponent(float M) { return 2 * kLimbBits - (ilogbf(M * 1.001f) + 1); }
+__device__ __forceinline__ float fixed_join(int lo, int hi, float inv_scale) {
+  return __ll2float_rn(((long long)hi << kLimbBits) + (long long)lo) * inv_scale;
+}
+
 __host__ __device__ inline int cl_pitch(int FG, int layout) { return layout == TILE_CLQ ? FG + 4 : (FG | 1); }
 
 inline int tile_array_words(int cells, int FG, int layout) {
@@ -314,11 +361,10 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     const float M = __int_as_float(counter[1]);
     fixed_point = counter[2] == 0;
     const int cnt_bits = 32 - __clz(cnt > 1 ? cnt - 1 : 1);   // cnt <= 2^cnt_bits
-    if (cnt_bits <= 11) limb_bits = 32 - cnt_bits;            // >= 41 magnitude bits: far below fp32 resolution
+    if (cnt_bits <= kLimbMaxCountBits) limb_bits = kLimbBits;  // 40 magnitude bits: far below fp32 resolution
     if (fixed_point && M > 0.0f) {
-      // carry-free limbs: |q| < 2^(2*limb_bits-1) per contribution (the count headroom is in the limbs);
-      // carried limbs: the whole sum must stay below 2^62
-      int k = limb_bits > 0 ? (2 * limb_bits - 1) - (ilogbf(M) + 1) : 62 - (ilogbf(M) + 1) - (cnt_bits + 1);
+      // carry-free limbs: see fixed_split; carried limbs: the whole sum must stay below 2^62
+      int k = limb_bits > 0 ? fixed_split_exponent(M) : 62 - (ilogbf(M) + 1) - (cnt_bits + 1);
       k = k > 120 ? 120 : k;
       scale = ldexpf(1.0f, k);
       inv_scale = ldexpf(1.0f, -k);
@@ -355,16 +401,16 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
       if (!has) {
         // idle lanes must not touch the tile (they would all hammer word 0)
       } else if (fixed_point && limb_bits > 0) {
-        const unsigned lmask = (1u << limb_bits) - 1u;
 #pragma unroll
         for (int f = 0; f < 4; ++f)
           if (f < fg)
 #pragma unroll
             for (int s = 0; s < S; ++s)
               if (w[s] != 0.0f) {
-                const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(ft[f], w[s]), scale));
-                atomicAdd((unsigned*)tval + a[s] + f * fs, (unsigned)q & lmask);
-                atomicAdd(targ + a[s] + f * fs, (int)(q >> limb_bits));
+                int qlo, qhi;
+                fixed_split(CTB_FMUL(CTB_FMUL(ft[f], w[s]), scale), qlo, qhi);
+                atomicAdd((int*)tval + a[s] + f * fs, qlo);
+                atomicAdd(targ + a[s] + f * fs, qhi);
               }
       } else {
 #pragma unroll
@@ -438,14 +484,14 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
           }
           if constexpr (SUM) {
             if (fixed_point && limb_bits > 0) {
-              const unsigned lmask = (1u << limb_bits) - 1u;
 #pragma unroll
               for (int s = 0; s < S; ++s)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(ft[j], w[s]), scale));
-                  atomicAdd((unsigned*)tval + a[s] + f + j, (unsigned)q & lmask);
-                  atomicAdd(targ + a[s] + f + j, (int)(q >> limb_bits));
+                  int qlo, qhi;
+                  fixed_split(CTB_FMUL(CTB_FMUL(ft[j], w[s]), scale), qlo, qhi);
+                  atomicAdd((int*)tval + a[s] + f + j, qlo);
+                  atomicAdd(targ + a[s] + f + j, qhi);
                 }
             } else {
 #pragma unroll
@@ -513,19 +559,17 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
       const float* fp = fu + n;
       if constexpr (SUM) {
         if (fixed_point && limb_bits > 0) {
-          // order-independent accumulation without carries: q = v * 2^k (|q| < 2^(2*limb_bits-1)) is split into
-          // an unsigned low limb and a signed high limb; cnt * 2^limb_bits <= 2^32, so neither sum can overflow
-          unsigned* lo_t = (unsigned*)tval;
-          const unsigned lmask = (1u << limb_bits) - 1u;
+          // order-independent accumulation without carries (fixed_split)
 #pragma unroll 2
           for (int f = 0; f < fg; ++f) {
             float ft = __ldg(fp + (size_t)f * N);
             if (pu) ft = CTB_FMUL(ft, pd);
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-              const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(ft, w[s]), scale));
-              atomicAdd(lo_t + a[s] + f * fs, (unsigned)q & lmask);
-              atomicAdd(targ + a[s] + f * fs, (int)(q >> limb_bits));
+              int qlo, qhi;
+              fixed_split(CTB_FMUL(CTB_FMUL(ft, w[s]), scale), qlo, qhi);
+              atomicAdd((int*)tval + a[s] + f * fs, qlo);
+              atomicAdd(targ + a[s] + f * fs, qhi);
             }
           }
         } else if (fixed_point) {
@@ -606,8 +650,8 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     return;
   }
   auto limbs_to_float = [&](float lo_bits, int hi) {
-    const long long lo = (long long)(unsigned)__float_as_int(lo_bits);
-    const long long q = limb_bits > 0 ? ((long long)hi << limb_bits) + lo : (((long long)hi << 32) | lo);
+    if (limb_bits > 0) return fixed_join(__float_as_int(lo_bits), hi, inv_scale);
+    const long long q = ((long long)hi << 32) | (long long)(unsigned)__float_as_int(lo_bits);
     return __ll2float_rn(q) * inv_scale;
   };
   if constexpr (LAYOUT == TILE_PM4 && F32) {

@@ -11,6 +11,13 @@
 //      turns "lane = point" loads into "lane = channel" reads), positions of the chunk (lane = point) -> shared
 //   B. every warp walks points of the chunk, lanes = channels (32 / LP points at a time for LP-lane groups)
 // Arithmetic and results are identical to tile_scatter_kernel (same products, integer max / min / add).
+//
+// Paired mode (PAR: groups of 9..16 channels, last grid axis even).  Two points share a warp step, 16 lanes each.
+// The cell pitch is 16 words, so a cell lives in banks 0-15 (even cell) or 16-31 (odd cell), and the parity of a
+// cell is the parity of its last-axis coordinate.  Each point has 2^(d-1) even and 2^(d-1) odd corners: the first
+// half-warp walks its point's even corners first, the second half-warp its odd corners first, so at every step the
+// two half-warps are in opposite bank halves -- no bank conflict on any atomic (ncu before: 40 % of the shared
+// wavefronts of the c3d sum were conflicts, r01_ncu_full_summary.csv).
 #pragma once
 #include "ctb_tile.cuh"
 
@@ -19,25 +26,27 @@ namespace ctb {
 constexpr int kClChunk = 128;   // points per chunk (power of two)
 
 __host__ __device__ inline int cl_stage_words(int FG) { return (FG * (kClChunk + 1) + 3) & ~3; }
-inline size_t cl_extra_bytes(int FG, int dim) {
-  return (size_t)cl_stage_words(FG) * 4 + (size_t)kClChunk * (1 << dim) * 8 + 16;
+// words of one staging buffer: features [FG][chunk+1], corner offsets and weights [chunk][2^d], flips [chunk]
+__host__ __device__ inline int cl_buffer_words(int FG, int dim) {
+  return cl_stage_words(FG) + kClChunk * (1 << dim) * 2 + kClChunk;
 }
+inline size_t cl_extra_bytes(int FG, int dim) { return (size_t)cl_buffer_words(FG, dim) * 4 * 2 + 16; }
 
-template <int D, bool SUM, typename GT>
+template <int D, bool SUM, bool PAR, typename GT>
 __global__ void __launch_bounds__(kTileThreads, 2)
 cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat, const float* __restrict__ pad,
                   GT* __restrict__ z, int* __restrict__ arg, Grid<D> g, int H, int F, int N, int FG, int groups,
                   int tw, int LP) {
   constexpr int S = 1 << D;
+  constexpr int HALF = S / 2;            // corner bit of the last (fastest) grid axis
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int fgp = cl_pitch(FG, TILE_CL);
+  const int fgp = PAR ? 16 : cl_pitch(FG, TILE_CL);
   const bool want_arg = !SUM && arg != nullptr;
   float* tval = (float*)smem_raw;                                    // max: value bits   | sum: low limb
   int* targ = (int*)(tval + tw);                                     // max: arg (if any) | sum: high limb
-  float* xs = (float*)(targ + ((SUM || want_arg) ? tw : 0));         // [FG][kClChunk + 1]
-  int* pa = (int*)(xs + cl_stage_words(FG));                         // [kClChunk][S] word offset of the corner cell
-  float* pw = (float*)(pa + kClChunk * S);                           // [kClChunk][S] corner weight
-  int* counter = (int*)(pw + kClChunk * S);                          // [1] max|v| bits, [2] non-finite
+  float* stage = (float*)(targ + ((SUM || want_arg) ? tw : 0));      // two staging buffers (double buffering)
+  const int bw = cl_buffer_words(FG, D);
+  int* counter = (int*)(stage + 2 * bw);                             // [1] max|v| bits, [2] non-finite
 
   const int f0 = (blockIdx.x % groups) * FG;
   const int unit = blockIdx.x / groups;
@@ -64,11 +73,14 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
   if constexpr (SUM) {
     float m = 0.0f;
     bool bad = false;
-    for (int i = threadIdx.x; i < fg * N; i += kTileThreads) {
-      const int n = i % N;
-      const float v = fabsf(__ldg(fu + i) * (pu ? __ldg(pu + n) : 1.0f));
-      bad |= !(v <= 3.0e38f);
-      m = fmaxf(m, v);
+    for (int n = threadIdx.x; n < N; n += kTileThreads) {
+      const float pd = pu ? __ldg(pu + n) : 1.0f;
+#pragma unroll 8
+      for (int f = 0; f < fg; ++f) {
+        const float v = fabsf(__ldg(fu + (size_t)f * N + n) * pd);
+        bad |= !(v <= 3.0e38f);
+        m = fmaxf(m, v);
+      }
     }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     bad = __any_sync(0xffffffffu, bad);
@@ -80,9 +92,9 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
     const float M = __int_as_float(counter[1]);
     fixed_point = counter[2] == 0;
     const int cnt_bits = 32 - __clz(N > 1 ? N - 1 : 1);
-    if (cnt_bits <= 11) limb_bits = 32 - cnt_bits;
+    if (cnt_bits <= kLimbMaxCountBits) limb_bits = kLimbBits;
     if (fixed_point && M > 0.0f) {
-      int k = limb_bits > 0 ? (2 * limb_bits - 1) - (ilogbf(M) + 1) : 62 - (ilogbf(M) + 1) - (cnt_bits + 1);
+      int k = limb_bits > 0 ? fixed_split_exponent(M) : 62 - (ilogbf(M) + 1) - (cnt_bits + 1);
       k = k > 120 ? 120 : k;
       scale = ldexpf(1.0f, k);
       inv_scale = ldexpf(1.0f, -k);
@@ -90,61 +102,104 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
   }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ch = lane % LP;                 // my channel inside the group
-  const int sub = lane / LP;                // which of the 32 / LP points of this warp step
-  const int ppw = 32 / LP;                  // points per warp step
+  const int lp_sh = __ffs(LP) - 1;          // LP is a power of two
+  const int ch = lane & (LP - 1);           // my channel inside the group
+  const int sub = lane >> lp_sh;            // which of the 32 / LP points of a warp step
   const bool ch_ok = ch < fg;
-  const unsigned lmask = limb_bits > 0 ? (1u << limb_bits) - 1u : 0u;
+
+  // Chunk pipeline: while the warps work through chunk c (shared atomics), the features and keys of chunk c+1 are
+  // already in flight into registers; they are staged into the other buffer afterwards -- one barrier per chunk
+  // and no exposed global-load latency.
+  constexpr int XR = PAR ? (16 * kClChunk / kTileThreads) : (32 * kClChunk / kTileThreads);   // feature regs / thread
+  const int nchunks = (N + kClChunk - 1) / kClChunk;
+  float nx[XR], nk[D], npd = 1.0f;          // (the chunk index j of a thread is the same for all its XR rows)
+  auto fetch = [&](int c) {                     // global -> registers
+    const int c0 = c * kClChunk, pcn = min(kClChunk, N - c0);
+#pragma unroll
+    for (int r = 0; r < XR; ++r) {
+      const int i = threadIdx.x + r * kTileThreads;
+      const int f = i / kClChunk, j = i % kClChunk;
+      nx[r] = (f < fg && j < pcn) ? __ldg(fu + (size_t)f * N + c0 + j) : 0.0f;
+    }
+    if (pu) npd = ((int)(threadIdx.x % kClChunk) < pcn) ? __ldg(pu + c0 + threadIdx.x % kClChunk) : 0.0f;
+    if ((int)threadIdx.x < pcn) {
+#pragma unroll
+      for (int a2 = 0; a2 < D; ++a2) nk[a2] = __ldg(ku + (size_t)a2 * N + c0 + threadIdx.x);
+    }
+  };
+  auto stage_chunk = [&](int c) {               // registers -> staging buffer c & 1
+    const int pcn = min(kClChunk, N - c * kClChunk);
+    float* xs = stage + (c & 1) * bw;
+    int* pa = (int*)(xs + cl_stage_words(FG));
+    float* pw = (float*)(pa + kClChunk * S);
+    int* pfl = (int*)(pw + kClChunk * S);
+#pragma unroll
+    for (int r = 0; r < XR; ++r) {
+      const int i = threadIdx.x + r * kTileThreads;
+      const int f = i / kClChunk, j = i % kClChunk;
+      if (f < fg) xs[f * (kClChunk + 1) + j] = pu ? CTB_FMUL(nx[r], npd) : nx[r];
+    }
+    if ((int)threadIdx.x < pcn) {
+      const Pos<D> p = point_pos_from_values<D>(nk, g);
+      // PAR: slots 0..HALF-1 hold the corners in even cells, HALF..S-1 those in odd cells
+      const int fl = PAR ? ((p.base & 1) ? HALF : 0) : 0;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        pa[threadIdx.x * S + (s ^ fl)] = (p.base + corner_offset<D>(g, s)) * fgp;
+        pw[threadIdx.x * S + (s ^ fl)] = corner_weight<D>(p, s);
+      }
+      if (PAR) pfl[threadIdx.x] = fl;
+    }
+  };
 
 #pragma unroll 1
   for (int pass = 0; pass < (want_arg ? 2 : 1); ++pass) {
+    fetch(0);
+    stage_chunk(0);
+    __syncthreads();
 #pragma unroll 1
-    for (int c0 = 0; c0 < N; c0 += kClChunk) {
+    for (int c = 0; c < nchunks; ++c) {
+      const int c0 = c * kClChunk;
       const int pcn = min(kClChunk, N - c0);
-      // A. stage features (coalesced along the points) and positions of the chunk
-      for (int i = threadIdx.x; i < fg * kClChunk; i += kTileThreads) {
-        const int f = i / kClChunk, j = i % kClChunk;
-        float v = 0.0f;
-        if (j < pcn) {
-          v = __ldg(fu + (size_t)f * N + c0 + j);
-          if (pu) v = CTB_FMUL(v, __ldg(pu + c0 + j));
-        }
-        xs[f * (kClChunk + 1) + j] = v;
-      }
-      if (threadIdx.x < pcn) {
-        const Pos<D> p = point_pos<D>(ku, c0 + threadIdx.x, N, g);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          pa[threadIdx.x * S + s] = (p.base + corner_offset<D>(g, s)) * fgp;
-          pw[threadIdx.x * S + s] = corner_weight<D>(p, s);
-        }
-      }
-      __syncthreads();
-      // B. lanes = channels
-      for (int j = warp * ppw + sub; j < pcn; j += (kTileThreads / 32) * ppw) {
-        if (!ch_ok) continue;
+      if (c + 1 < nchunks) fetch(c + 1);
+      const float* xs = stage + (c & 1) * bw;
+      const int* pa = (const int*)(xs + cl_stage_words(FG));
+      const float* pw = (const float*)(pa + kClChunk * S);
+      const int* pfl = (const int*)(pw + kClChunk * S);
+      // lanes = channels.  A warp step takes the points j, j + LP, j + 2 LP .. so that the staged feature reads of
+      // its point groups fall into different banks.
+      for (int it = warp; it < (kClChunk / 32) * LP; it += kTileThreads / 32) {
+        const int j = ((it >> lp_sh) << 5) + (it & (LP - 1)) + (sub << lp_sh);
+        if (!ch_ok || j >= pcn) continue;
         const float x = xs[ch * (kClChunk + 1) + j];
         int a[S];
         float w[S];
+        const int hs = PAR ? sub : 0;      // second half-warp starts with the odd-cell corners
         if constexpr (S == 8) {
-          const int4 a0 = reinterpret_cast<const int4*>(pa)[j * 2], a1 = reinterpret_cast<const int4*>(pa)[j * 2 + 1];
-          const float4 w0 = reinterpret_cast<const float4*>(pw)[j * 2], w1 = reinterpret_cast<const float4*>(pw)[j * 2 + 1];
+          const int4 a0 = reinterpret_cast<const int4*>(pa)[j * 2 + hs], a1 = reinterpret_cast<const int4*>(pa)[j * 2 + (hs ^ 1)];
+          const float4 w0 = reinterpret_cast<const float4*>(pw)[j * 2 + hs], w1 = reinterpret_cast<const float4*>(pw)[j * 2 + (hs ^ 1)];
           a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
           w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
         } else {
-          const int4 a0 = reinterpret_cast<const int4*>(pa)[j];
-          const float4 w0 = reinterpret_cast<const float4*>(pw)[j];
-          a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-          w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
+          const int2 a0 = reinterpret_cast<const int2*>(pa)[j * 2 + hs], a1 = reinterpret_cast<const int2*>(pa)[j * 2 + (hs ^ 1)];
+          const float2 w0 = reinterpret_cast<const float2*>(pw)[j * 2 + hs], w1 = reinterpret_cast<const float2*>(pw)[j * 2 + (hs ^ 1)];
+          a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y;
+          w[0] = w0.x; w[1] = w0.y; w[2] = w1.x; w[3] = w1.y;
         }
         const int n = c0 + j;
         if constexpr (SUM) {
           if (fixed_point && limb_bits > 0) {
+            const float xsc = CTB_FMUL(x, scale);      // power-of-two scale: same product bits as (x * w) * scale
+            int* const lo_b = (int*)tval + ch;
+            int* const hi_b = targ + ch;
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(x, w[s]), scale));
-              atomicAdd((unsigned*)tval + a[s] + ch, (unsigned)q & lmask);
-              atomicAdd(targ + a[s] + ch, (int)(q >> limb_bits));
+            for (int s = 0; s < S; s += 2) {
+              int l0, h0, l1, h1;
+              fixed_split2(xsc, w[s], w[s + 1], l0, h0, l1, h1);
+              atomicAdd(lo_b + a[s], l0);
+              atomicAdd(hi_b + a[s], h0);
+              atomicAdd(lo_b + a[s + 1], l1);
+              atomicAdd(hi_b + a[s + 1], h1);
             }
           } else if (fixed_point) {
 #pragma unroll
@@ -173,25 +228,51 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
             any |= hit[s];
           }
           if (any) {
+            const int sx = PAR ? (pfl[j] ^ (hs ? HALF : 0)) : 0;      // slot -> corner number
 #pragma unroll
             for (int s = 0; s < S; ++s)
-              if (hit[s]) atomicMin((unsigned*)targ + a[s] + ch, (unsigned)(s * N + n));
+              if (hit[s]) atomicMin((unsigned*)targ + a[s] + ch, (unsigned)((s ^ sx) * N + n));
           }
         }
       }
+      if (c + 1 < nchunks) stage_chunk(c + 1);
       __syncthreads();
     }
   }
 
   GT* zu = z + ((size_t)unit * F + f0) * g.C;
   int* au = want_arg ? arg + ((size_t)unit * F + f0) * g.C : nullptr;
+  if constexpr (PAR) {
+    // pitch 16: lanes along the cells read four channels at a time (16-byte shared loads), stores stay coalesced
+    const int C = g.C;
+    for (int i = threadIdx.x; i < C * 4; i += kTileThreads) {
+      const int r = i % C, qd = i / C;
+      if (qd * 4 >= fg) continue;
+      const float4 v4 = reinterpret_cast<const float4*>(tval)[r * 4 + qd];
+      const int4 h4 = (SUM || want_arg) ? reinterpret_cast<const int4*>(targ)[r * 4 + qd] : make_int4(0, 0, 0, 0);
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+      const int hh[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int f = qd * 4 + k;
+        if (f >= fg) break;
+        float v1 = vv[k];
+        if (SUM && fixed_point) {
+          if (limb_bits > 0) v1 = fixed_join(__float_as_int(v1), hh[k], inv_scale);
+          else v1 = __ll2float_rn(((long long)hh[k] << 32) | (long long)(unsigned)__float_as_int(v1)) * inv_scale;
+        }
+        grid_store(zu + (size_t)f * C + r, v1);
+        if (want_arg) __stcs(au + (size_t)f * C + r, hh[k]);
+      }
+    }
+    return;
+  }
   for_each_plane_element(fg, g.C, [&](int f, int r) {
     float v1 = tval[r * fgp + f];
     if (SUM && fixed_point) {
-      const long long lo = (long long)(unsigned)__float_as_int(v1);
       const int hi = targ[r * fgp + f];
-      const long long q = limb_bits > 0 ? ((long long)hi << limb_bits) + lo : (((long long)hi << 32) | lo);
-      v1 = __ll2float_rn(q) * inv_scale;
+      if (limb_bits > 0) v1 = fixed_join(__float_as_int(v1), hi, inv_scale);
+      else v1 = __ll2float_rn(((long long)hi << 32) | (long long)(unsigned)__float_as_int(v1)) * inv_scale;
     }
     grid_store(zu + (size_t)f * g.C + r, v1);
     if (want_arg) __stcs(au + (size_t)f * g.C + r, targ[r * fgp + f]);
@@ -217,22 +298,25 @@ bool cl_scatter_try(const float* keys, const float* feat, const float* pad, GT* 
   groups = (s->F + FG - 1) / FG;
   int LP = 1;
   while (LP < FG) LP <<= 1;
-  const int tw = tile_array_words(cells, FG, TILE_CL);
+  const bool par = LP == 16 && (s->size[s->dim - 1] % 2) == 0 && getenv("CTB_CL_NO_PAIRING") == nullptr;
+  const int tw = par ? cells * 16 : tile_array_words(cells, FG, TILE_CL);
   const size_t smem = bytes(FG);
   const Grid<D> g = make_grid<D>(s->size);
   const long long blocks = (long long)s->B * s->H * groups;
   if (blocks >= (1ll << 31)) return false;
+  auto launch = [&](auto kernel) {
+    *err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (*err != cudaSuccess) return;
+    kernel<<<(unsigned)blocks, kTileThreads, smem, stream>>>(keys, feat, pad, z, arg, g, s->H, s->F, s->N, FG, groups, tw, LP);
+  };
   if (sum) {
-    *err = cudaFuncSetAttribute(cl_scatter_kernel<D, true, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (*err != cudaSuccess) return true;
-    cl_scatter_kernel<D, true, GT><<<(unsigned)blocks, kTileThreads, smem, stream>>>(keys, feat, pad, z, arg, g, s->H, s->F,
-                                                                               s->N, FG, groups, tw, LP);
+    if (par) launch(cl_scatter_kernel<D, true, true, GT>);
+    else launch(cl_scatter_kernel<D, true, false, GT>);
   } else {
-    *err = cudaFuncSetAttribute(cl_scatter_kernel<D, false, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (*err != cudaSuccess) return true;
-    cl_scatter_kernel<D, false, GT><<<(unsigned)blocks, kTileThreads, smem, stream>>>(keys, feat, pad, z, arg, g, s->H, s->F,
-                                                                                s->N, FG, groups, tw, LP);
+    if (par) launch(cl_scatter_kernel<D, false, true, GT>);
+    else launch(cl_scatter_kernel<D, false, false, GT>);
   }
+  if (*err != cudaSuccess) return true;
   *err = cudaGetLastError();
   return true;
 }

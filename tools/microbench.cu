@@ -33,6 +33,37 @@ __global__ void smem_kernel(float* out) {
   if (MODE == 3 && acc == 12345.f) out[0] = acc;
 }
 
+// address patterns of the channel-lane kernels: lanes = channels of one cell (consecutive words)
+// PAT 0: 32 lanes on one random 32-word row     1: two half-warps on two random 16-word cells (pitch 16, any parity)
+// PAT 2: as 1 but opposite parities (no conflict) 3: two half-warps, pitch 17     4: all lanes one word
+// OP 0 atomicAdd s32, 1 atomicMax s32, 2 load, 3 two atomicAdd s32 into two arrays (the two-limb sum)
+template <int OP, int PAT>
+__global__ void smem_lane_kernel(float* out) {
+  __shared__ int tile[TILE];
+  for (int i = threadIdx.x; i < TILE; i += blockDim.x) tile[i] = 0;
+  __syncthreads();
+  uint32_t s = blockIdx.x * 7919u + (threadIdx.x >> 5) * 104729u + 1u;   // warp-uniform stream
+  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  int acc = 0;
+  for (int it = 0; it < ITERS; ++it) {
+    const uint32_t r0 = lcg(s), r1 = lcg(s);
+    int a;
+    if (PAT == 0) a = (r0 & (TILE / 2 / 32 - 1)) * 32 + lane;
+    else if (PAT == 1) a = ((half ? r1 : r0) & (TILE / 2 / 16 - 1)) * 16 + l16;
+    else if (PAT == 2) a = ((((half ? r1 : r0) & (TILE / 2 / 32 - 1)) << 1) | half) * 16 + l16;
+    else if (PAT == 3) a = ((half ? r1 : r0) & 127) * 17 + l16;
+    else a = r0 & (TILE / 2 - 1);
+    const int v = (int)(s & 1023u) + lane;
+    if (OP == 0) atomicAdd(&tile[a], v);
+    else if (OP == 1) atomicMax(&tile[a], v);
+    else if (OP == 2) acc += tile[a];
+    else { atomicAdd(&tile[a], v); atomicAdd(&tile[a + TILE / 2], v >> 3); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)(tile[5] + acc);
+  if (OP == 2 && acc == 12345) out[0] = (float)acc;
+}
+
 template <int MODE>  // 0 red.max.s32, 1 red.add.f32, 2 red.add.v4.f32, 3 scattered 4B load, 4 scattered 4B store
 __global__ void gmem_kernel(float* buf, size_t n_elems, float* out, int iters) {
   uint32_t s = blockIdx.x * 7919u + threadIdx.x * 104729u + 1u;
@@ -70,6 +101,24 @@ int main() {
   const int sms = p.multiProcessorCount;
   printf("device %s, %d SMs, clock %d kHz\n", p.name, sms, p.clockRate);
   float* out; CK(cudaMalloc(&out, 1 << 20));
+  {
+    const int blocks = sms * 2, threads = 512;
+    const double lane_ops = (double)blocks * threads * ITERS;
+    auto rep = [&](const char* name, float ms, double mult) {
+      printf("%-58s %8.3f ms  %7.3f lane-ops/clk/SM\n", name, ms, lane_ops * mult / (ms * 1e-3) / sms / (p.clockRate * 1e3));
+    };
+    rep("smem lanes atomicAdd.s32  1 row of 32 words", time_ms([&] { smem_lane_kernel<0, 0><<<blocks, threads>>>(out); }), 1);
+    rep("smem lanes atomicAdd.s32  2 cells pitch 16 random", time_ms([&] { smem_lane_kernel<0, 1><<<blocks, threads>>>(out); }), 1);
+    rep("smem lanes atomicAdd.s32  2 cells pitch 16 opposite parity", time_ms([&] { smem_lane_kernel<0, 2><<<blocks, threads>>>(out); }), 1);
+    rep("smem lanes atomicAdd.s32  2 cells pitch 17", time_ms([&] { smem_lane_kernel<0, 3><<<blocks, threads>>>(out); }), 1);
+    rep("smem lanes atomicAdd.s32  all lanes one word", time_ms([&] { smem_lane_kernel<0, 4><<<blocks, threads>>>(out); }), 1);
+    rep("smem lanes atomicMax.s32  1 row of 32 words", time_ms([&] { smem_lane_kernel<1, 0><<<blocks, threads>>>(out); }), 1);
+    rep("smem lanes atomicMax.s32  2 cells pitch 16 opposite parity", time_ms([&] { smem_lane_kernel<1, 2><<<blocks, threads>>>(out); }), 1);
+    rep("smem lanes load           1 row of 32 words", time_ms([&] { smem_lane_kernel<2, 0><<<blocks, threads>>>(out); }), 1);
+    rep("smem lanes load           2 cells pitch 17", time_ms([&] { smem_lane_kernel<2, 3><<<blocks, threads>>>(out); }), 1);
+    rep("smem lanes 2x atomicAdd   1 row of 32 words (per atomic)", time_ms([&] { smem_lane_kernel<3, 0><<<blocks, threads>>>(out); }), 2);
+    rep("smem lanes 2x atomicAdd   2 cells opposite parity (per atomic)", time_ms([&] { smem_lane_kernel<3, 2><<<blocks, threads>>>(out); }), 2);
+  }
   const char* sn[4] = {"smem atomicMax.s32 random", "smem atomicAdd.f32 random", "smem plain RMW max random", "smem plain load random"};
   for (int ctas = 1; ctas <= 2; ++ctas) {
     const int blocks = sms * ctas, threads = 512;
