@@ -137,6 +137,23 @@ __device__ __forceinline__ void fixed_split2(float x, float w0, float w1, int& l
   lo0 = (int)(unsigned)(r & 0xffffffffull) - kRoundMagicBits;
   lo1 = (int)(unsigned)(r >> 32) - kRoundMagicBits;
 }
+// Raw variant: returns the packed float pairs u = magic + hi, r = magic + lo.  Their bit patterns are
+// kRoundMagicBits + hi / + lo, so a kernel that also counts the contributions per cell can add the raw words
+// (wrap-around arithmetic) and subtract count * kRoundMagicBits once at read-out -- no per-element integer op.
+__device__ __forceinline__ void fixed_split2_raw(float x, float w0, float w1, unsigned long long& u, unsigned long long& r) {
+  const unsigned long long xx = pack_f32x2(x, x), ww = pack_f32x2(w0, w1);
+  const unsigned long long magic = pack_f32x2(kRoundMagic, kRoundMagic), nmagic = pack_f32x2(-kRoundMagic, -kRoundMagic);
+  const unsigned long long dn = pack_f32x2(0x1p-20f, 0x1p-20f), nup = pack_f32x2(-0x1p20f, -0x1p20f);
+  unsigned long long t, hf, rem;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(xx), "l"(ww));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(u) : "l"(t), "l"(dn), "l"(magic));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(hf) : "l"(u), "l"(nmagic));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rem) : "l"(hf), "l"(nup), "l"(t));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(rem), "l"(magic));
+}
+__device__ __forceinline__ void red_shared_add_u32(unsigned addr, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 // scale exponent for the two-limb format: max|v| * 2^k <= 2^40 / 1.001, so that |hi| stays below 2^20
 __device__ __forceinline__ int fixed_split_exponent(float M) { return 2 * kLimbBits - (ilogbf(M * 1.001f) + 1); }
 __device__ __forceinline__ float fixed_join(int lo, int hi, float inv_scale) {

@@ -30,7 +30,9 @@ __host__ __device__ inline int cl_stage_words(int FG) { return (FG * (kClChunk +
 __host__ __device__ inline int cl_buffer_words(int FG, int dim) {
   return cl_stage_words(FG) + kClChunk * (1 << dim) * 2 + kClChunk;
 }
-inline size_t cl_extra_bytes(int FG, int dim) { return (size_t)cl_buffer_words(FG, dim) * 4 * 2 + 16; }
+inline size_t cl_extra_bytes(int FG, int dim, int cells) {          // + per-cell contribution counts (sum)
+  return (size_t)cl_buffer_words(FG, dim) * 4 * 2 + 16 + (size_t)((cells + 3) & ~3) * 4;
+}
 
 template <int D, bool SUM, bool PAR, typename GT>
 __global__ void __launch_bounds__(kTileThreads, 2)
@@ -47,6 +49,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
   float* stage = (float*)(targ + ((SUM || want_arg) ? tw : 0));      // two staging buffers (double buffering)
   const int bw = cl_buffer_words(FG, D);
   int* counter = (int*)(stage + 2 * bw);                             // [1] max|v| bits, [2] non-finite
+  int* ccnt = counter + 4;                                           // sum: contributions per cell
 
   const int f0 = (blockIdx.x % groups) * FG;
   const int unit = blockIdx.x / groups;
@@ -59,6 +62,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
       if (SUM) a4[i] = make_int4(0, 0, 0, 0);
       else if (want_arg) a4[i] = make_int4(-1, -1, -1, -1);
     }
+    if (SUM) for (int i = threadIdx.x; i < g.C; i += kTileThreads) ccnt[i] = 0;
     if (threadIdx.x == 0) counter[1] = counter[2] = 0;
   }
   const float* ku = keys + (size_t)unit * D * N;
@@ -102,10 +106,12 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
   }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lp_sh = __ffs(LP) - 1;          // LP is a power of two
+  if (PAR) LP = 16;                          // (compile-time constant in the paired kernels)
+  const int lp_sh = PAR ? 4 : __ffs(LP) - 1; // LP is a power of two
   const int ch = lane & (LP - 1);           // my channel inside the group
   const int sub = lane >> lp_sh;            // which of the 32 / LP points of a warp step
   const bool ch_ok = ch < fg;
+  const unsigned lo_base = smem_u32(tval) + (unsigned)ch * 4u, hi_off = (unsigned)tw * 4u;
 
   // Chunk pipeline: while the warps work through chunk c (shared atomics), the features and keys of chunk c+1 are
   // already in flight into registers; they are staged into the other buffer afterwards -- one barrier per chunk
@@ -115,13 +121,14 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
   float nx[XR], nk[D], npd = 1.0f;          // (the chunk index j of a thread is the same for all its XR rows)
   auto fetch = [&](int c) {                     // global -> registers
     const int c0 = c * kClChunk, pcn = min(kClChunk, N - c0);
+    // thread -> (row f = tid / chunk + r * rows_per_sweep, point j = tid % chunk): j is the same for all r
+    const int j = threadIdx.x % kClChunk, fb = threadIdx.x / kClChunk;
+    const float* src = fu + (size_t)fb * N + c0 + j;
+    const bool jok = j < pcn;
 #pragma unroll
-    for (int r = 0; r < XR; ++r) {
-      const int i = threadIdx.x + r * kTileThreads;
-      const int f = i / kClChunk, j = i % kClChunk;
-      nx[r] = (f < fg && j < pcn) ? __ldg(fu + (size_t)f * N + c0 + j) : 0.0f;
-    }
-    if (pu) npd = ((int)(threadIdx.x % kClChunk) < pcn) ? __ldg(pu + c0 + threadIdx.x % kClChunk) : 0.0f;
+    for (int r = 0; r < XR; ++r)
+      nx[r] = (jok && fb + r * (kTileThreads / kClChunk) < fg) ? __ldg(src + (size_t)r * (kTileThreads / kClChunk) * N) : 0.0f;
+    if (pu) npd = jok ? __ldg(pu + c0 + j) : 0.0f;
     if ((int)threadIdx.x < pcn) {
 #pragma unroll
       for (int a2 = 0; a2 < D; ++a2) nk[a2] = __ldg(ku + (size_t)a2 * N + c0 + threadIdx.x);
@@ -147,6 +154,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
       for (int s = 0; s < S; ++s) {
         pa[threadIdx.x * S + (s ^ fl)] = (p.base + corner_offset<D>(g, s)) * fgp;
         pw[threadIdx.x * S + (s ^ fl)] = corner_weight<D>(p, s);
+        if (SUM) atomicAdd(ccnt + p.base + corner_offset<D>(g, s), 1);
       }
       if (PAR) pfl[threadIdx.x] = fl;
     }
@@ -189,17 +197,17 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
         const int n = c0 + j;
         if constexpr (SUM) {
           if (fixed_point && limb_bits > 0) {
+            // raw limb words (magic + limb): the per-cell counts take the magic back out at read-out
             const float xsc = CTB_FMUL(x, scale);      // power-of-two scale: same product bits as (x * w) * scale
-            int* const lo_b = (int*)tval + ch;
-            int* const hi_b = targ + ch;
 #pragma unroll
             for (int s = 0; s < S; s += 2) {
-              int l0, h0, l1, h1;
-              fixed_split2(xsc, w[s], w[s + 1], l0, h0, l1, h1);
-              atomicAdd(lo_b + a[s], l0);
-              atomicAdd(hi_b + a[s], h0);
-              atomicAdd(lo_b + a[s + 1], l1);
-              atomicAdd(hi_b + a[s + 1], h1);
+              unsigned long long u, r;
+              fixed_split2_raw(xsc, w[s], w[s + 1], u, r);
+              const unsigned a0 = lo_base + ((unsigned)a[s] << 2), a1 = lo_base + ((unsigned)a[s + 1] << 2);
+              red_shared_add_u32(a0, (unsigned)r);
+              red_shared_add_u32(a0 + hi_off, (unsigned)u);
+              red_shared_add_u32(a1, (unsigned)(r >> 32));
+              red_shared_add_u32(a1 + hi_off, (unsigned)(u >> 32));
             }
           } else if (fixed_point) {
 #pragma unroll
@@ -258,7 +266,8 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
         if (f >= fg) break;
         float v1 = vv[k];
         if (SUM && fixed_point) {
-          if (limb_bits > 0) v1 = fixed_join(__float_as_int(v1), hh[k], inv_scale);
+          const unsigned back = (unsigned)ccnt[r] * (unsigned)kRoundMagicBits;
+          if (limb_bits > 0) v1 = fixed_join((int)((unsigned)__float_as_int(v1) - back), (int)((unsigned)hh[k] - back), inv_scale);
           else v1 = __ll2float_rn(((long long)hh[k] << 32) | (long long)(unsigned)__float_as_int(v1)) * inv_scale;
         }
         grid_store(zu + (size_t)f * C + r, v1);
@@ -271,7 +280,8 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
     float v1 = tval[r * fgp + f];
     if (SUM && fixed_point) {
       const int hi = targ[r * fgp + f];
-      if (limb_bits > 0) v1 = fixed_join(__float_as_int(v1), hi, inv_scale);
+      const unsigned back = (unsigned)ccnt[r] * (unsigned)kRoundMagicBits;
+      if (limb_bits > 0) v1 = fixed_join((int)((unsigned)__float_as_int(v1) - back), (int)((unsigned)hi - back), inv_scale);
       else v1 = __ll2float_rn(((long long)hi << 32) | (long long)(unsigned)__float_as_int(v1)) * inv_scale;
     }
     grid_store(zu + (size_t)f * g.C + r, v1);
@@ -290,7 +300,7 @@ bool cl_scatter_try(const float* keys, const float* feat, const float* pad, GT* 
   // re-fit the channel group with the staging buffers included
   int FG = c.FG > 32 ? 32 : c.FG;
   const int cells = s->size[0] * (s->dim == 2 ? s->size[1] : s->size[1] * s->size[2]);
-  auto bytes = [&](int fg) { return (size_t)tile_array_words(cells, fg, TILE_CL) * 4 * arrays + cl_extra_bytes(fg, s->dim); };
+  auto bytes = [&](int fg) { return (size_t)tile_array_words(cells, fg, TILE_CL) * 4 * arrays + cl_extra_bytes(fg, s->dim, cells); };
   while (FG > 1 && bytes(FG) > (size_t)kTileSmemTwoCtas) --FG;
   if (bytes(FG) > (size_t)kTileSmemTwoCtas || FG < 4) return false;
   int groups = (s->F + FG - 1) / FG;
