@@ -556,9 +556,43 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   } else
 #pragma unroll 1
   for (int pass = 0; pass < (want_arg ? 2 : 1); ++pass) {
+    // one point of software prefetch: keys, pad and the first kPrefetchCh features of the thread's NEXT point are
+    // in flight while the current point works on the tile (ncu r01: the dependent load -> atomic chains were the
+    // top stall of the class-b scatters)
+    constexpr int kPrefetchCh = 4;
+    int nn = 0;
+    float nk[D], npd = 1.0f, nft[kPrefetchCh];
+    auto prefetch = [&](int i) {
+      nn = slabs > 1 ? (int)sel[i] : i;
+#pragma unroll
+      for (int a2 = 0; a2 < D; ++a2) nk[a2] = __ldg(ku + (size_t)a2 * N + nn);
+      if (pu) npd = __ldg(pu + nn);
+#pragma unroll
+      for (int q = 0; q < kPrefetchCh; ++q) nft[q] = q < fg ? __ldg(fu + (size_t)q * N + nn) : 0.0f;
+    };
+    if ((int)threadIdx.x < cnt) prefetch(threadIdx.x);
     for (int i = threadIdx.x; i < cnt; i += kTileThreads) {
-      const int n = slabs > 1 ? (int)sel[i] : i;
-      const Pos<D> p = point_pos<D>(ku, n, N, g);
+      const int n = nn;
+      const float pd = npd;
+      float kv[D], ft0[kPrefetchCh];
+#pragma unroll
+      for (int a2 = 0; a2 < D; ++a2) kv[a2] = nk[a2];
+#pragma unroll
+      for (int q = 0; q < kPrefetchCh; ++q) ft0[q] = pu ? CTB_FMUL(nft[q], pd) : nft[q];
+      if (i + kTileThreads < cnt) prefetch(i + kTileThreads);
+      const Pos<D> p = point_pos_from_values<D>(kv, g);
+      // run body(f, feature * pad) over the channels of the group: registers first, then the rest from global
+      auto for_channels = [&](auto&& body) {
+#pragma unroll
+        for (int q = 0; q < kPrefetchCh; ++q)
+          if (q < fg) body(q, ft0[q]);
+#pragma unroll 2
+        for (int f = kPrefetchCh; f < fg; ++f) {
+          float ft = __ldg(fu + (size_t)f * N + n);
+          if (pu) ft = CTB_FMUL(ft, pd);
+          body(f, ft);
+        }
+      };
       const bool in0 = (p.c0 >= x0) && (p.c0 < x1);
       const bool in1 = (p.c0 + 1 >= x0) && (p.c0 + 1 < x1);
       // corners outside the slab are redirected to their in-slab sibling (other row) with weight 0:
@@ -572,31 +606,26 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
         w[s] = ins ? corner_weight<D>(p, s) : 0.0f;
         a[s] = lc * cs;
       }
-      const float pd = pu ? __ldg(pu + n) : 1.0f;
-      const float* fp = fu + n;
       if constexpr (SUM) {
         if (fixed_point && limb_bits > 0) {
           // order-independent accumulation without carries (fixed_split)
-#pragma unroll 2
-          for (int f = 0; f < fg; ++f) {
-            float ft = __ldg(fp + (size_t)f * N);
-            if (pu) ft = CTB_FMUL(ft, pd);
+          for_channels([&](int f, float ft) {
+            const float fsc = CTB_FMUL(ft, scale);     // power-of-two scale: same bits as (ft * w) * scale
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
-              int qlo, qhi;
-              fixed_split(CTB_FMUL(CTB_FMUL(ft, w[s]), scale), qlo, qhi);
-              atomicAdd((int*)tval + a[s] + f * fs, qlo);
-              atomicAdd(targ + a[s] + f * fs, qhi);
+            for (int s = 0; s < S; s += 2) {
+              int l0, h0, l1, h1;
+              fixed_split2(fsc, w[s], w[s + 1], l0, h0, l1, h1);
+              atomicAdd((int*)tval + a[s] + f * fs, l0);
+              atomicAdd(targ + a[s] + f * fs, h0);
+              atomicAdd((int*)tval + a[s + 1] + f * fs, l1);
+              atomicAdd(targ + a[s + 1] + f * fs, h1);
             }
-          }
+          });
         } else if (fixed_point) {
           // exact, order-independent accumulation: q = v * 2^k as int64, added as (lo, hi) 32-bit limbs with the
           // carry taken from the value the lo atomic returns; sum of carries == number of lo wrap-arounds
           unsigned* lo_t = (unsigned*)tval;
-#pragma unroll 2
-          for (int f = 0; f < fg; ++f) {
-            float ft = __ldg(fp + (size_t)f * N);
-            if (pu) ft = CTB_FMUL(ft, pd);
+          for_channels([&](int f, float ft) {
 #pragma unroll
             for (int s = 0; s < S; ++s) {
               const long long q = __float2ll_rn(CTB_FMUL(CTB_FMUL(ft, w[s]), scale));
@@ -605,31 +634,22 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
               const int hi = (int)(q >> 32) + ((unsigned)(old + lo) < old ? 1 : 0);
               if (hi != 0) atomicAdd(targ + a[s] + f * fs, hi);
             }
-          }
+          });
         } else {
-#pragma unroll 2
-          for (int f = 0; f < fg; ++f) {
-            float ft = __ldg(fp + (size_t)f * N);
-            if (pu) ft = CTB_FMUL(ft, pd);
+          for_channels([&](int f, float ft) {
 #pragma unroll
             for (int s = 0; s < S; ++s)
               if (w[s] != 0.0f) atomicAdd(tval + a[s] + f * fs, CTB_FMUL(ft, w[s]));
-          }
+          });
         }
       } else if (pass == 0) {
-#pragma unroll 4
-        for (int f = 0; f < fg; ++f) {
-          float ft = __ldg(fp + (size_t)f * N);
-          if (pu) ft = CTB_FMUL(ft, pd);
+        for_channels([&](int f, float ft) {
 #pragma unroll
           for (int s = 0; s < S; ++s)
             atomicMax((int*)tval + a[s] + f * fs, __float_as_int(fmaxf(CTB_FMUL(ft, w[s]), 0.0f)));
-        }
+        });
       } else {
-#pragma unroll 4
-        for (int f = 0; f < fg; ++f) {
-          float ft = __ldg(fp + (size_t)f * N);
-          if (pu) ft = CTB_FMUL(ft, pd);
+        for_channels([&](int f, float ft) {
           // winners are rare: test all corners branch-free first, take the atomic path only if one matched
           bool hit[S];
           bool any = false;
@@ -644,7 +664,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
             for (int s = 0; s < S; ++s)
               if (hit[s]) atomicMin((unsigned*)targ + a[s] + f * fs, (unsigned)(s * N + n));
           }
-        }
+        });
       }
     }
     __syncthreads();
@@ -918,11 +938,29 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
         }
       }
     } else
+    {
+    // one point of software prefetch for the keys and pad of the thread's next point
+    int nn = 0;
+    float nk[D], npd = 1.0f;
+    auto prefetch = [&](int i) {
+      nn = slabs > 1 ? (int)sel[i] : i;
+#pragma unroll
+      for (int a2 = 0; a2 < D; ++a2) nk[a2] = __ldg(ku + (size_t)a2 * N + nn);
+      if (pu) npd = __ldg(pu + nn);
+    };
+    // (only where it fits the 64-register budget of two 512-thread CTAs per SM; the backward modes would spill)
+    constexpr bool kAhead = MODE == GATHER_SLICE_FWD;
+    if (kAhead && (int)threadIdx.x < cnt) prefetch(threadIdx.x);
 #pragma unroll 1
     for (int i = threadIdx.x; i < cnt; i += kTileThreads) {
-      const int n = slabs > 1 ? (int)sel[i] : i;
-      const Pos<D> p = point_pos<D>(ku, n, N, g);
-      const float pd = pu ? __ldg(pu + n) : 1.0f;
+      if (!kAhead) prefetch(i);
+      const int n = nn;
+      const float pd = npd;
+      float kv[D];
+#pragma unroll
+      for (int a2 = 0; a2 < D; ++a2) kv[a2] = nk[a2];
+      if (kAhead && i + kTileThreads < cnt) prefetch(i + kTileThreads);
+      const Pos<D> p = point_pos_from_values<D>(kv, g);
       float w[S];
       int a[S];
 #pragma unroll
@@ -978,6 +1016,7 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
           *gp = f0 == 0 ? part[a2] : *gp + part[a2];
         }
       }
+    }
     }
   }
 }
