@@ -359,13 +359,21 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   if constexpr (SUM) {
     float m = 0.0f;
     bool bad = false;
+    // (loads in batches of four channels, two points per trip: eight independent loads in flight per thread)
+#pragma unroll 2
     for (int i = threadIdx.x; i < cnt; i += kTileThreads) {
       const int n = slabs > 1 ? (int)sel[i] : i;
       const float pd = pu ? __ldg(pu + n) : 1.0f;
-      for (int f = 0; f < fg; ++f) {
-        const float v = fabsf(__ldg(fu + (size_t)f * N + n) * pd);
-        bad |= !(v <= 3.0e38f);
-        m = fmaxf(m, v);
+      for (int f = 0; f < fg; f += 4) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = f + q < fg ? __ldg(fu + (size_t)(f + q) * N + n) : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float av = fabsf(v[q] * pd);
+          bad |= !(av <= 3.0e38f);
+          m = fmaxf(m, av);
+        }
       }
     }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));

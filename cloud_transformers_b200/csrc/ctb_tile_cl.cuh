@@ -79,11 +79,16 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
     bool bad = false;
     for (int n = threadIdx.x; n < N; n += kTileThreads) {
       const float pd = pu ? __ldg(pu + n) : 1.0f;
-#pragma unroll 8
-      for (int f = 0; f < fg; ++f) {
-        const float v = fabsf(__ldg(fu + (size_t)f * N + n) * pd);
-        bad |= !(v <= 3.0e38f);
-        m = fmaxf(m, v);
+      for (int f = 0; f < fg; f += 8) {       // eight independent loads in flight per thread
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = f + q < fg ? __ldg(fu + (size_t)(f + q) * N + n) : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float av = fabsf(v[q] * pd);
+          bad |= !(av <= 3.0e38f);
+          m = fmaxf(m, av);
+        }
       }
     }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
