@@ -302,20 +302,26 @@ bool cl_scatter_try(const float* keys, const float* feat, const float* pad, GT* 
   if (!tile_scatter_config(s, sum, arg != nullptr, &c)) return false;
   if ((c.layout != TILE_CL && c.layout != TILE_CLQ) || c.slabs != 1) return false;
   const int arrays = (sum || arg != nullptr) ? 2 : 1;
-  // re-fit the channel group with the staging buffers included
-  int FG = c.FG > 32 ? 32 : c.FG;
+  // re-fit the channel group with the staging buffers included; 9..16 channels on an even last axis run paired
+  // (cell pitch 16), everything else with the odd pitch FG | 1
+  static const bool no_pairing = getenv("CTB_CL_NO_PAIRING") != nullptr;
+  const bool even_last = (s->size[s->dim - 1] % 2) == 0;
   const int cells = s->size[0] * (s->dim == 2 ? s->size[1] : s->size[1] * s->size[2]);
-  auto bytes = [&](int fg) { return (size_t)tile_array_words(cells, fg, TILE_CL) * 4 * arrays + cl_extra_bytes(fg, s->dim, cells); };
+  auto lanes = [](int fg) { int lp = 1; while (lp < fg) lp <<= 1; return lp; };
+  auto paired = [&](int fg) { return lanes(fg) == 16 && even_last && !no_pairing; };
+  auto tile_words = [&](int fg) { return paired(fg) ? cells * 16 : tile_array_words(cells, fg, TILE_CL); };
+  auto bytes = [&](int fg) { return (size_t)tile_words(fg) * 4 * arrays + cl_extra_bytes(fg, s->dim, cells); };
+  int FG = c.FG > 32 ? 32 : c.FG;
   while (FG > 1 && bytes(FG) > (size_t)kTileSmemTwoCtas) --FG;
   if (bytes(FG) > (size_t)kTileSmemTwoCtas || FG < 4) return false;
   int groups = (s->F + FG - 1) / FG;
   FG = (s->F + groups - 1) / groups;
   groups = (s->F + FG - 1) / FG;
-  int LP = 1;
-  while (LP < FG) LP <<= 1;
-  const bool par = LP == 16 && (s->size[s->dim - 1] % 2) == 0 && getenv("CTB_CL_NO_PAIRING") == nullptr;
-  const int tw = par ? cells * 16 : tile_array_words(cells, FG, TILE_CL);
+  const int LP = lanes(FG);
+  const bool par = paired(FG);
+  const int tw = tile_words(FG);
   const size_t smem = bytes(FG);
+  if (smem > (size_t)kTileSmemTwoCtas) return false;
   const Grid<D> g = make_grid<D>(s->size);
   const long long blocks = (long long)s->B * s->H * groups;
   if (blocks >= (1ll << 31)) return false;

@@ -352,8 +352,11 @@ def test_tile_sum_is_order_independent_and_accurate():
     is associative): the result is bit-identical from run to run AND invariant under any permutation of the
     points -- stronger than a fixed summation order -- and closer to the exact sum than float accumulation:
     |err| <= 2^-24 |exact| + N * 2^-39 * max|feature|."""
+    # the last four rows walk the channel-lane kernel's variants: paired half-warps with idle channel lanes and a
+    # ragged last chunk, odd last axis (unpaired), 8-lane groups, and the paired 2-D case
     for dim, W, H, F, N, B in [(3, 8, 2, 32, 2048, 2), (2, 64, 2, 16, 2048, 1), (3, 32, 2, 4, 2048, 1),
-                               (2, 16, 2, 8, 5000, 1)]:
+                               (2, 16, 2, 8, 5000, 1), (3, 8, 2, 12, 1000, 1), (3, (8, 8, 7), 2, 16, 777, 1),
+                               (2, 16, 2, 5, 300, 2), (2, 16, 2, 16, 2048, 1)]:
         keys, feat, pad = make_inputs(31, B, H, dim, F, N, pad=True)
         geom = CF.Geometry(O._sizes(W, dim), H, dim)
         rng = np.random.default_rng(4)
@@ -377,6 +380,26 @@ def test_tile_sum_is_order_independent_and_accurate():
         err = np.abs(outs[0].astype(np.float64) - ex)
         bound = 2.0 ** -24 * np.abs(ex) + N * 2.0 ** -39 * float(np.abs(feat).max())
         assert (err <= bound).all(), float((err - bound).max())
+
+
+def test_tile_sum_limb_headroom_worst_case():
+    """Every one of the 2048 points sits exactly on one grid node (corner weight 1) and carries the largest
+    mantissa: the per-cell limb sums reach their design maximum.  The sum 2048 * (2 - 2^-23) is representable, so
+    the result must be exact -- any overflow of a 32-bit limb would show."""
+    big = np.float32(2.0) - np.float32(2.0 ** -23)
+    for dim, W, F in [(3, 5, 16), (2, 65, 4), (2, 9, 16)]:
+        N, H, B = 2048, 1, 1
+        keys = np.full((B, H * dim, N), -0.5, np.float32)          # (k + 1) * (W - 1) / 2 is an integer
+        for sign in (1.0, -1.0):
+            feat = np.full((B, H * F, N), sign * big, np.float32)
+            ctb.config.mode = "tile"
+            h = CF.PositionsHandle(t(keys), CF.Geometry(O._sizes(W, dim), H, dim))
+            with torch.no_grad():
+                z = n(CF.fused_splat(h, t(feat), None, _lib.REDUCE_SUM))
+            node = (W - 1) // 4
+            want = np.zeros_like(z)
+            want[(0, slice(None)) + (node,) * dim] = np.float32(sign) * (np.float32(4096.0) - np.float32(2.0 ** -12))
+            assert np.array_equal(z, want), (dim, W, F, sign, float(np.abs(z - want).max()))
 
 
 # --- A8: fused projection + tanh, and the MHCT block mirror ------------------------------------------
