@@ -36,7 +36,11 @@
 
 namespace ctb {
 
-constexpr int kTileThreads = 512;
+constexpr int kTileThreads = 512;   // launch bound; the actual CTA size is blockDim.x (tile_threads())
+inline int tile_threads() {
+  static const int t = getenv("CTB_TILE_THREADS") ? atoi(getenv("CTB_TILE_THREADS")) : kTileThreads;
+  return (t == 128 || t == 256 || t == 512) ? t : kTileThreads;
+}
 constexpr int kTileSmemTwoCtas = 110 * 1024;
 constexpr int kTileSmemMax = 220 * 1024;
 constexpr int kTileMaxPoints = 65535;  // compacted point lists are uint16
@@ -256,16 +260,16 @@ __device__ __forceinline__ int compact_slab_points(const float* __restrict__ ku,
   __syncthreads();
   const int lane = threadIdx.x & 31;
   constexpr int kBatch = 4;   // keys of 4 rounds are fetched together: one L2 round trip instead of four
-  for (int n0 = 0; n0 < N; n0 += kTileThreads * kBatch) {
+  for (int n0 = 0; n0 < N; n0 += (int)blockDim.x * kBatch) {
     float kx[kBatch];
 #pragma unroll
     for (int b = 0; b < kBatch; ++b) {
-      const int n = n0 + b * kTileThreads + threadIdx.x;
+      const int n = n0 + b * (int)blockDim.x + threadIdx.x;
       kx[b] = n < N ? __ldg(ku + n) : 0.0f;
     }
 #pragma unroll
     for (int b = 0; b < kBatch; ++b) {
-      const int n = n0 + b * kTileThreads + threadIdx.x;
+      const int n = n0 + b * (int)blockDim.x + threadIdx.x;
       bool take = false;
       if (n < N) {
         bool in_rng;
@@ -294,7 +298,7 @@ __device__ __forceinline__ void for_each_plane_element(int fg, int count, Fn fn)
   int r = threadIdx.x - f * count;
   while (f < fg) {
     fn(f, r);
-    r += kTileThreads;
+    r += (int)blockDim.x;
     while (r >= count) {
       r -= count;
       ++f;
@@ -336,7 +340,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   {
     float4* t4 = reinterpret_cast<float4*>(tval);
     int4* a4 = reinterpret_cast<int4*>(targ);
-    for (int i = threadIdx.x; i < (tw >> 2); i += kTileThreads) {
+    for (int i = threadIdx.x; i < (tw >> 2); i += (int)blockDim.x) {
       t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (SUM) a4[i] = make_int4(0, 0, 0, 0);
       else if (want_arg) a4[i] = make_int4(-1, -1, -1, -1);   // "no winner" == max unsigned
@@ -361,7 +365,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     bool bad = false;
     // (loads in batches of four channels, two points per trip: eight independent loads in flight per thread)
 #pragma unroll 2
-    for (int i = threadIdx.x; i < cnt; i += kTileThreads) {
+    for (int i = threadIdx.x; i < cnt; i += (int)blockDim.x) {
       const int n = slabs > 1 ? (int)sel[i] : i;
       const float pd = pu ? __ldg(pu + n) : 1.0f;
       for (int f = 0; f < fg; f += 4) {
@@ -396,7 +400,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     }
   }
 
-  if (!CL && slabs > 1 && cnt <= kTileThreads && fg <= 4) {
+  if (!CL && slabs > 1 && cnt <= (int)blockDim.x && fg <= 4) {
     // Sparse-grid slab (class a): at most one point per thread.  All global loads (keys, features) are issued up
     // front in one batch, and the arg pass reuses the registers of the max pass -- no second trip to L2.
     const bool has = (int)threadIdx.x < cnt;
@@ -488,7 +492,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     const int lpp = 1 << lsh;
 #pragma unroll 1
     for (int pass = 0; pass < (want_arg ? 2 : 1); ++pass) {
-      for (int slot = threadIdx.x; slot < (cnt << lsh); slot += kTileThreads) {
+      for (int slot = threadIdx.x; slot < (cnt << lsh); slot += (int)blockDim.x) {
         const int n = slot >> lsh, q0 = slot & (lpp - 1);
         const Pos<D> p = point_pos<D>(ku, n, N, g);
         float w[S];
@@ -579,7 +583,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
       for (int q = 0; q < kPrefetchCh; ++q) nft[q] = q < fg ? __ldg(fu + (size_t)q * N + nn) : 0.0f;
     };
     if ((int)threadIdx.x < cnt) prefetch(threadIdx.x);
-    for (int i = threadIdx.x; i < cnt; i += kTileThreads) {
+    for (int i = threadIdx.x; i < cnt; i += (int)blockDim.x) {
       const int n = nn;
       const float pd = npd;
       float kv[D], ft0[kPrefetchCh];
@@ -587,7 +591,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
       for (int a2 = 0; a2 < D; ++a2) kv[a2] = nk[a2];
 #pragma unroll
       for (int q = 0; q < kPrefetchCh; ++q) ft0[q] = pu ? CTB_FMUL(nft[q], pd) : nft[q];
-      if (i + kTileThreads < cnt) prefetch(i + kTileThreads);
+      if (i + (int)blockDim.x < cnt) prefetch(i + (int)blockDim.x);
       const Pos<D> p = point_pos_from_values<D>(kv, g);
       // run body(f, feature * pad) over the channels of the group: registers first, then the rest from global
       auto for_channels = [&](auto&& body) {
@@ -740,7 +744,7 @@ cudaError_t launch_tile_scatter(const float* keys, const float* feat, const floa
   cudaError_t e = cudaFuncSetAttribute(tile_scatter_kernel<D, SUM, LAYOUT, GT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
-  tile_scatter_kernel<D, SUM, LAYOUT, GT><<<(unsigned)blocks, kTileThreads, c.smem, stream>>>(
+  tile_scatter_kernel<D, SUM, LAYOUT, GT><<<(unsigned)blocks, tile_threads(), c.smem, stream>>>(
       keys, feat, pad, z, arg, g, s->H, s->F, s->N, c.FG, c.R, c.slabs, groups, c.words);
   return cudaGetLastError();
 }
@@ -847,7 +851,7 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
       const int lsh = qn >= 4 ? 2 : (qn >= 2 ? 1 : 0);
       const int lpp = 1 << lsh;
 #pragma unroll 1
-      for (int slot = threadIdx.x; slot < (cnt << lsh); slot += kTileThreads) {
+      for (int slot = threadIdx.x; slot < (cnt << lsh); slot += (int)blockDim.x) {
         const unsigned active = __activemask();
         const int n = slot >> lsh, q0 = slot & (lpp - 1);
         const Pos<D> p = point_pos<D>(ku, n, N, g);
@@ -960,14 +964,14 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
     constexpr bool kAhead = MODE == GATHER_SLICE_FWD;
     if (kAhead && (int)threadIdx.x < cnt) prefetch(threadIdx.x);
 #pragma unroll 1
-    for (int i = threadIdx.x; i < cnt; i += kTileThreads) {
+    for (int i = threadIdx.x; i < cnt; i += (int)blockDim.x) {
       if (!kAhead) prefetch(i);
       const int n = nn;
       const float pd = npd;
       float kv[D];
 #pragma unroll
       for (int a2 = 0; a2 < D; ++a2) kv[a2] = nk[a2];
-      if (kAhead && i + kTileThreads < cnt) prefetch(i + kTileThreads);
+      if (kAhead && i + (int)blockDim.x < cnt) prefetch(i + (int)blockDim.x);
       const Pos<D> p = point_pos_from_values<D>(kv, g);
       float w[S];
       int a[S];
@@ -990,12 +994,24 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
           out[po + (size_t)f * N] = acc;
         }
       } else if constexpr (MODE == GATHER_SLICE_BWD_KEYS) {
-#pragma unroll 4
-        for (int f = 0; f < fg; ++f) {
-          float go = __ldg(in + po + (size_t)f * N);
-          if (pu) go *= pd;
+        // the upstream gradients run one batch of four channels ahead of the shared-memory work
+        float gn[4];
 #pragma unroll
-          for (int s = 0; s < S; ++s) gw[s] = fmaf(s1[a[s] + f * fs], go, gw[s]);
+        for (int q = 0; q < 4; ++q) gn[q] = q < fg ? __ldg(in + po + (size_t)q * N) : 0.0f;
+#pragma unroll 1
+        for (int f = 0; f < fg; f += 4) {
+          float gc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gc[q] = pu ? gn[q] * pd : gn[q];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gn[q] = f + 4 + q < fg ? __ldg(in + po + (size_t)(f + 4 + q) * N) : 0.0f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (f + q < fg) {
+#pragma unroll
+              for (int s = 0; s < S; ++s) gw[s] = fmaf(s1[a[s] + (f + q) * fs], gc[q], gw[s]);
+            }
+          }
         }
       } else {
 #pragma unroll 2
@@ -1043,7 +1059,7 @@ cudaError_t launch_gather(const float* keys, const GT* t1, const int* t2, const 
   cudaError_t e = cudaFuncSetAttribute(tile_gather_kernel<D, MODE, LAYOUT, GT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
-  tile_gather_kernel<D, MODE, LAYOUT, GT><<<(unsigned)blocks, kTileThreads, c.smem, stream>>>(
+  tile_gather_kernel<D, MODE, LAYOUT, GT><<<(unsigned)blocks, tile_threads(), c.smem, stream>>>(
       keys, t1, t2, in, pad, out, grad_keys, g, s->H, s->F, s->N, c.FG, c.R, c.slabs, c.words);
   return cudaGetLastError();
 }
