@@ -785,7 +785,11 @@ template <int D, int MODE, int LAYOUT, typename GT>
 __global__ void __launch_bounds__(kTileThreads, 2)
 tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, const int* __restrict__ t2,
                    const float* __restrict__ in, const float* __restrict__ pad, float* __restrict__ out,
-                   float* __restrict__ grad_keys, Grid<D> g, int H, int F, int N, int FG, int R, int slabs, int tw) {
+                   float* __restrict__ grad_keys, Grid<D> g, int H, int F, int N, int FG, int R, int slabs, int tw,
+                   int gsplit) {
+  // gsplit CTAs share the channel groups of one (unit, slab): Slice forward gives every group its own CTA (more,
+  // shorter CTAs: better balance over the SMs and tile loads that overlap other CTAs' gathers); the backward modes
+  // keep gsplit == 1 because one thread accumulates grad_keys over the groups in a fixed order.
   constexpr int S = 1 << D;
   constexpr bool CL = LAYOUT == TILE_CL || LAYOUT == TILE_CLQ;
   constexpr bool TMA = LAYOUT == TILE_PM4 && std::is_same<GT, float>::value;   // raw tile copy by the copy engine
@@ -801,8 +805,9 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
   int* counter = (int*)(sel + ((N + 7) & ~7));
   uint64_t* bar = (uint64_t*)(counter + 4);     // 16-byte aligned: the list is padded to 8 entries
 
-  const int slab = blockIdx.x % slabs;
-  const int unit = blockIdx.x / slabs;
+  const int gi = blockIdx.x % gsplit;
+  const int slab = (blockIdx.x / gsplit) % slabs;
+  const int unit = blockIdx.x / (gsplit * slabs);
   const int x0 = slab * R;
   const int x1 = min(x0 + R, W0 - 1);           // base rows [x0, x1)
   const int xe = min(x1 + 1, W0);               // tile rows [x0, xe)
@@ -819,9 +824,10 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
   if (!TMA && slabs > 1) cnt = compact_slab_points<D, false>(ku, N, g, x0, x1, sel, counter);
 
   uint32_t parity = 0;
-  for (int f0 = 0; f0 < F; f0 += FG) {
+  for (int f0 = gi * FG; f0 < F; f0 += FG * gsplit) {
     const int fg = min(FG, F - f0);
-    if (f0 > 0) __syncthreads();                 // previous group's readers are done with the tile
+    const bool first = f0 == gi * FG;
+    if (!first) __syncthreads();                 // previous group's readers are done with the tile
     const GT* g1 = t1 + ((size_t)unit * F + f0) * g.C + cell0;
     const int* g2 = MODE == GATHER_SPLAT_BWD ? t2 + ((size_t)unit * F + f0) * g.C + cell0 : nullptr;
     if constexpr (TMA) {
@@ -835,7 +841,7 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
             bulk_g2s(s2 + (size_t)f * tile_cells, g2 + (size_t)f * g.C, plane_bytes, bar);
         }
       }
-      if (f0 == 0 && slabs > 1) cnt = compact_slab_points<D, false>(ku, N, g, x0, x1, sel, counter);
+      if (first && slabs > 1) cnt = compact_slab_points<D, false>(ku, N, g, x0, x1, sel, counter);
       mbar_wait(bar, parity);
       parity ^= 1u;
     } else {
@@ -1054,13 +1060,15 @@ template <int D, int MODE, int LAYOUT, typename GT>
 cudaError_t launch_gather(const float* keys, const GT* t1, const int* t2, const float* in, const float* pad,
                           float* out, float* grad_keys, const ctb_shape* s, const TileConfig& c, cudaStream_t stream) {
   const Grid<D> g = make_grid<D>(s->size);
-  const long long blocks = (long long)s->B * s->H * c.slabs;
+  static const bool no_split = getenv("CTB_GATHER_NO_SPLIT") != nullptr;
+  const int gsplit = (MODE == GATHER_SLICE_FWD && !no_split) ? (s->F + c.FG - 1) / c.FG : 1;
+  const long long blocks = (long long)s->B * s->H * c.slabs * gsplit;
   if (blocks >= (1ll << 31)) return cudaErrorNotSupported;
   cudaError_t e = cudaFuncSetAttribute(tile_gather_kernel<D, MODE, LAYOUT, GT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
   tile_gather_kernel<D, MODE, LAYOUT, GT><<<(unsigned)blocks, tile_threads(), c.smem, stream>>>(
-      keys, t1, t2, in, pad, out, grad_keys, g, s->H, s->F, s->N, c.FG, c.R, c.slabs, c.words);
+      keys, t1, t2, in, pad, out, grad_keys, g, s->H, s->F, s->N, c.FG, c.R, c.slabs, c.words, gsplit);
   return cudaGetLastError();
 }
 
