@@ -155,6 +155,18 @@ __device__ __forceinline__ void fixed_split2_raw(float x, float w0, float w1, un
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rem) : "l"(hf), "l"(nup), "l"(t));
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(rem), "l"(magic));
 }
+// shared-memory loads through 32-bit shared-window addresses: keeps nvcc from rebuilding the generic address
+// (S2R SR_CgaCtaId + shifts) next to every predicated tile access
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void red_shared_add_u32(unsigned addr, unsigned v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -801,6 +813,7 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
   const int fs = CL ? 1 : tile_cells;
   float* s1 = (float*)smem_raw;
   int* s2 = (int*)(s1 + tw);                                        // (SPLAT_BWD: arg)
+  const unsigned s1_base = smem_u32(s1), s12 = (unsigned)tw << 2;   // shared-window address of s1; byte distance to s2
   unsigned short* sel = (unsigned short*)(s2 + (MODE == GATHER_SPLAT_BWD ? tw : 0));
   int* counter = (int*)(sel + ((N + 7) & ~7));
   uint64_t* bar = (uint64_t*)(counter + 4);     // 16-byte aligned: the list is padded to 8 entries
@@ -990,12 +1003,18 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
 #pragma unroll
       for (int s = 0; s < S; ++s) gw[s] = 0.0f;
       const size_t po = ((size_t)unit * F + f0) * N + n;
+      // byte addresses of the point's corner cells in the shared window; channel f adds f * fstep
+      unsigned ab[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) ab[s] = s1_base + ((unsigned)a[s] << 2);
+      const unsigned fstep = (unsigned)fs << 2;
       if constexpr (MODE == GATHER_SLICE_FWD) {
 #pragma unroll 4
         for (int f = 0; f < fg; ++f) {
-          float acc = CTB_FMUL(s1[a[0] + f * fs], w[0]);
+          const unsigned off = (unsigned)f * fstep;
+          float acc = CTB_FMUL(lds_f32(ab[0] + off), w[0]);
 #pragma unroll
-          for (int s = 1; s < S; ++s) acc = fmaf(s1[a[s] + f * fs], w[s], acc);
+          for (int s = 1; s < S; ++s) acc = fmaf(lds_f32(ab[s] + off), w[s], acc);
           if (pu) acc = CTB_FMUL(acc, pd);
           out[po + (size_t)f * N] = acc;
         }
@@ -1014,26 +1033,42 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (f + q < fg) {
+              const unsigned off = (unsigned)(f + q) * fstep;
 #pragma unroll
-              for (int s = 0; s < S; ++s) gw[s] = fmaf(s1[a[s] + (f + q) * fs], gc[q], gw[s]);
+              for (int s = 0; s < S; ++s) gw[s] = fmaf(lds_f32(ab[s] + off), gc[q], gw[s]);
             }
           }
         }
       } else {
-#pragma unroll 2
-        for (int f = 0; f < fg; ++f) {
-          float ft = __ldg(in + po + (size_t)f * N);
-          if (pu) ft *= pd;
-          float gf = 0.0f;
+        // features run one batch of two channels ahead of the shared-memory work
+        float fn[2];
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            const bool win = s2[a[s] + f * fs] == s * N + n;
-            const float gz = win ? s1[a[s] + f * fs] : 0.0f;
-            gf = fmaf(gz, w[s], gf);
-            gw[s] = fmaf(gz, ft, gw[s]);
+        for (int q = 0; q < 2; ++q) fn[q] = q < fg ? __ldg(in + po + (size_t)q * N) : 0.0f;
+#pragma unroll 1
+        for (int f = 0; f < fg; f += 2) {
+          float fc[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) fc[q] = pu ? fn[q] * pd : fn[q];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) fn[q] = f + 2 + q < fg ? __ldg(in + po + (size_t)(f + 2 + q) * N) : 0.0f;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (f + q < fg) {
+              float gf = 0.0f;
+              const unsigned off = (unsigned)(f + q) * fstep;
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                const unsigned ad = ab[s] + off;
+                const bool win = lds_s32(ad + s12) == s * N + n;
+                float gz = 0.0f;
+                if (win) gz = lds_f32(ad);
+                gf = fmaf(gz, w[s], gf);
+                gw[s] = fmaf(gz, fc[q], gw[s]);
+              }
+              if (pu) gf *= pd;
+              out[po + (size_t)(f + q) * N] = gf;
+            }
           }
-          if (pu) gf *= pd;
-          out[po + (size_t)f * N] = gf;
         }
       }
       if constexpr (MODE != GATHER_SLICE_FWD) {
