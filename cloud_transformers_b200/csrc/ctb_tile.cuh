@@ -869,12 +869,27 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
       const int qn = fg >> 2;
       const int lsh = qn >= 4 ? 2 : (qn >= 2 ? 1 : 0);
       const int lpp = 1 << lsh;
+      // Slice forward: keys and pad of the thread's next slot are fetched one slot ahead
+      constexpr bool kAheadQ = MODE == GATHER_SLICE_FWD;
+      float nk[D], npd = 1.0f;
+      auto prefetch = [&](int slot) {
+        const int n = slot >> lsh;
+#pragma unroll
+        for (int a2 = 0; a2 < D; ++a2) nk[a2] = __ldg(ku + (size_t)a2 * N + n);
+        if (pu) npd = __ldg(pu + n);
+      };
+      if (kAheadQ && (int)threadIdx.x < (cnt << lsh)) prefetch(threadIdx.x);
 #pragma unroll 1
       for (int slot = threadIdx.x; slot < (cnt << lsh); slot += (int)blockDim.x) {
         const unsigned active = __activemask();
         const int n = slot >> lsh, q0 = slot & (lpp - 1);
-        const Pos<D> p = point_pos<D>(ku, n, N, g);
-        const float pd = pu ? __ldg(pu + n) : 1.0f;
+        if (!kAheadQ) prefetch(slot);
+        const float pd = npd;
+        float kv[D];
+#pragma unroll
+        for (int a2 = 0; a2 < D; ++a2) kv[a2] = nk[a2];
+        if (kAheadQ && slot + (int)blockDim.x < (cnt << lsh)) prefetch(slot + (int)blockDim.x);
+        const Pos<D> p = point_pos_from_values<D>(kv, g);
         float w[S], gw[S];
         int a[S];
 #pragma unroll
