@@ -205,6 +205,19 @@ extern "C" {
 
 int ctb_version(void) { return CTB_VERSION; }
 
+#ifdef CTB_PHASE_TIMERS
+// developer tool (not in the header): copy out / reset the phase cycle counters of ctb_tile.cuh
+int ctb_debug_phase(unsigned long long* host16, int reset) {
+  cudaDeviceSynchronize();
+  if (host16 && cudaMemcpyFromSymbol(host16, ctb::g_phase, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(ctb::g_phase, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#endif
+
 const char* ctb_strerror(int status) {
   switch (status) {
     case CTB_OK: return "ok";

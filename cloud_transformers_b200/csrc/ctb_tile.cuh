@@ -36,6 +36,24 @@
 
 namespace ctb {
 
+// Developer tool: build with -DCTB_PHASE_TIMERS to accumulate, per CTA (thread 0), the clock64 cycles between the
+// phase boundaries of tile_scatter_kernel into g_phase[] (read with ctb_debug_phase()).
+#ifdef CTB_PHASE_TIMERS
+__device__ unsigned long long g_phase[16];
+#define CTB_STAMP(i)                                                         \
+  do {                                                                       \
+    if (threadIdx.x == 0) {                                                  \
+      const long long t_now = clock64();                                     \
+      atomicAdd(&g_phase[i], (unsigned long long)(t_now - t_prev));          \
+      t_prev = t_now;                                                        \
+    }                                                                        \
+  } while (0)
+#define CTB_STAMP_INIT long long t_prev = clock64()
+#else
+#define CTB_STAMP(i) do { } while (0)
+#define CTB_STAMP_INIT do { } while (0)
+#endif
+
 constexpr int kTileThreads = 512;   // launch bound; the actual CTA size is blockDim.x (tile_threads())
 inline int tile_threads() {
   static const int t = getenv("CTB_TILE_THREADS") ? atoi(getenv("CTB_TILE_THREADS")) : kTileThreads;
@@ -339,6 +357,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   unsigned short* sel = (unsigned short*)(targ + ((SUM || want_arg) ? tw : 0));
   int* counter = (int*)(sel + ((N + 7) & ~7));                      // [0] compaction, [1] max|v| bits, [2] non-finite
 
+  CTB_STAMP_INIT;
   int item = blockIdx.x;
   const int slab = item % slabs;
   item /= slabs;
@@ -363,8 +382,10 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   const float* pu = pad ? pad + (size_t)(unit / H) * N : nullptr;
   const float* fu = feat + ((size_t)unit * F + f0) * N;
   int cnt = N;
+  CTB_STAMP(0);                                  // tile init (issue only)
   if (slabs > 1) cnt = compact_slab_points<D, true>(ku, N, g, x0, x1, sel, counter);
   else __syncthreads();
+  CTB_STAMP(1);                                  // compaction (+ init drained)
 
   // sum: pick the fixed-point scale 2^k from M = max |feature * pad| of this item, so that cnt * M * 2^k < 2^62
   // (|w| <= 1, a point hits a cell at most once).  Any k gives the same exact integer sum, so the result does not
@@ -412,6 +433,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
     }
   }
 
+  CTB_STAMP(2);                                  // sum prepass
   if (!CL && slabs > 1 && cnt <= (int)blockDim.x && fg <= 4) {
     // Sparse-grid slab (class a): at most one point per thread.  All global loads (keys, features) are issued up
     // front in one batch, and the arg pass reuses the registers of the max pass -- no second trip to L2.
@@ -427,6 +449,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
       if (pu) ft[f] = CTB_FMUL(ft[f], pd);
     }
     const Pos<D> p = point_pos_from_values<D>(kv, g);
+    CTB_STAMP(3);                                // global loads of the point (thread 0's)
     const bool in0 = has && (p.c0 >= x0) && (p.c0 < x1);
     const bool in1 = has && (p.c0 + 1 >= x0) && (p.c0 + 1 < x1);
     float w[S];
@@ -482,6 +505,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
               atomicMax((int*)tval + a[s] + f * fs, __float_as_int(fmaxf(CTB_FMUL(ft[f], w[s]), 0.0f)));
       }
       __syncthreads();
+      CTB_STAMP(4);                              // max pass
       if (want_arg) {
 #pragma unroll
         for (int f = 0; f < 4; ++f)
@@ -493,6 +517,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
                 atomicMin((unsigned*)targ + a[s] + f * fs, (unsigned)(s * N + n));
             }
         __syncthreads();
+        CTB_STAMP(5);                            // arg pass
       }
     }
   } else if constexpr (LAYOUT == TILE_CLQ) {
@@ -699,8 +724,16 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   int* au = want_arg ? arg + ((size_t)unit * F + f0) * g.C + cell0 : nullptr;
   if constexpr (LAYOUT == TILE_PM4 && !SUM && F32) {
     // the tile already holds the final bits of z (and arg): hand it to the copy engine, plane by plane
+#ifdef CTB_FENCE_SPLIT
+    CTB_STAMP(8);
+    fence_proxy_async();
+    CTB_STAMP(9);
+    __syncthreads();
+#else
     fence_proxy_async();
     __syncthreads();
+#endif
+    CTB_STAMP(6);                                // (generic-path passes end here too)
     if (threadIdx.x == 0) {
       for (int f = 0; f < fg; ++f) {
         bulk_s2g((float*)zu + (size_t)f * g.C, tval + (size_t)f * tile_cells, (uint32_t)ncell * 4u);
@@ -708,6 +741,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
       }
       bulk_commit_and_wait_read();
     }
+    CTB_STAMP(7);                                // TMA store until the tile has been read
     return;
   }
   auto limbs_to_float = [&](float lo_bits, int hi) {
