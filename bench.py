@@ -416,7 +416,10 @@ def run_train(args, dev, world, rank):
         model = ScanObjectTrunk().to(dev)
         if world > 1:
             model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index])
+            # SyncBN keeps the running statistics identical on all ranks, so the per-step buffer broadcast of stock
+            # DDP is redundant; gradients are reduced in place in the buckets
+            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=False,
+                                                              gradient_as_bucket_view=True)
         opt = torch.optim.Adam(model.parameters(), lr=1e-3)
         gen = torch.Generator(device=dev).manual_seed(7 + rank)
         clouds = [surface_clouds(gen, B, N_PTS, dev).cpu().pin_memory() for _ in range(4)]
@@ -433,7 +436,7 @@ def run_train(args, dev, world, rank):
             opt.step()
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
 
-        for i in range(3):
+        for i in range(5 if world > 1 else 3):      # (DDP rebuilds its buckets after the first step)
             step(i)
         if world > 1:
             dist.barrier()
