@@ -53,8 +53,10 @@ typedef enum ctb_reduce { CTB_REDUCE_MAX = 0, CTB_REDUCE_SUM = 1 } ctb_reduce;
  *                 independent, the arg winner is resolved by a min-e pass); float sums are not.
  *   TILE          CTA-owned shared-memory tiles of the grid: scatters accumulate with native
  *                 shared-memory atomics and store every cell once (no zero-fill, no L2 atomics), gathers
- *                 stage the slab with coalesced 16-byte loads.  Splat-max is reproducible; the float
- *                 sums (Slice backward grad_grid, Splat-sum) depend on warp scheduling.  The fast path.
+ *                 receive the slab by TMA bulk copy.  Splat-max is reproducible; the sums (Slice backward
+ *                 grad_grid, Splat-sum) are accumulated as exact fixed-point integers (|err| <= 2^-24 |sum|
+ *                 + N 2^-39 max|v|), so they are bit-identical from run to run and under any permutation of
+ *                 the points; only inputs with Inf / NaN fall back to float atomics.  The fast path.
  *   DETERMINISTIC as TILE, but the two scatters walk entries sorted by destination cell (needs a plan,
  *                 see ctb_plan_build): every cell is reduced by one owner in ascending e = s*N + n with
  *                 plain stores -- no atomics anywhere, bit-identical from run to run. */
