@@ -285,12 +285,13 @@ inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* ou
 // lies in [x0, x1).
 template <int D, bool BOTH_ROWS>
 __device__ __forceinline__ int compact_slab_points(const float* __restrict__ ku, int N, const Grid<D>& g, int x0, int x1,
-                                                   unsigned short* sel, int* counter) {
+                                                   unsigned short* sel, int* counter, int n_begin = 0) {
+  // points n_begin <= n < N are scanned (a CTA that shares its work item with others passes its own range)
   if (threadIdx.x == 0) *counter = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   constexpr int kBatch = 4;   // keys of 4 rounds are fetched together: one L2 round trip instead of four
-  for (int n0 = 0; n0 < N; n0 += (int)blockDim.x * kBatch) {
+  for (int n0 = n_begin; n0 < N; n0 += (int)blockDim.x * kBatch) {
     float kx[kBatch];
 #pragma unroll
     for (int b = 0; b < kBatch; ++b) {
@@ -832,7 +833,9 @@ __global__ void __launch_bounds__(kTileThreads, 2)
 tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, const int* __restrict__ t2,
                    const float* __restrict__ in, const float* __restrict__ pad, float* __restrict__ out,
                    float* __restrict__ grad_keys, Grid<D> g, int H, int F, int N, int FG, int R, int slabs, int tw,
-                   int gsplit) {
+                   int gsplit, int psplit) {
+  // psplit CTAs share the POINTS of one (unit, slab, group set): used when B * H is too small to fill the GPU
+  // (every CTA loads the tile, L2 serves the repeats).
   // gsplit CTAs share the channel groups of one (unit, slab): Slice forward gives every group its own CTA (more,
   // shorter CTAs: better balance over the SMs and tile loads that overlap other CTAs' gathers); the backward modes
   // keep gsplit == 1 because one thread accumulates grad_keys over the groups in a fixed order.
@@ -853,8 +856,9 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
   uint64_t* bar = (uint64_t*)(counter + 4);     // 16-byte aligned: the list is padded to 8 entries
 
   const int gi = blockIdx.x % gsplit;
-  const int slab = (blockIdx.x / gsplit) % slabs;
-  const int unit = blockIdx.x / (gsplit * slabs);
+  const int pi = (blockIdx.x / gsplit) % psplit;
+  const int slab = (blockIdx.x / (gsplit * psplit)) % slabs;
+  const int unit = blockIdx.x / (gsplit * psplit * slabs);
   const int x0 = slab * R;
   const int x1 = min(x0 + R, W0 - 1);           // base rows [x0, x1)
   const int xe = min(x1 + 1, W0);               // tile rows [x0, xe)
@@ -867,8 +871,11 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
   }
-  int cnt = N;
-  if (!TMA && slabs > 1) cnt = compact_slab_points<D, false>(ku, N, g, x0, x1, sel, counter);
+  // my share of the unit's points (by point index, so that the CTAs of an item agree on the partition)
+  const int per_n = (N + psplit - 1) / psplit;
+  const int n_lo = min(N, pi * per_n), n_hi = min(N, pi * per_n + per_n);
+  int cnt = n_hi - n_lo;      // slabs == 1: points n_lo + i; slabs > 1: the compacted list of my range
+  if (!TMA && slabs > 1) cnt = compact_slab_points<D, false>(ku, n_hi, g, x0, x1, sel, counter, n_lo);
 
   uint32_t parity = 0;
   for (int f0 = gi * FG; f0 < F; f0 += FG * gsplit) {
@@ -888,7 +895,7 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
             bulk_g2s(s2 + (size_t)f * tile_cells, g2 + (size_t)f * g.C, plane_bytes, bar);
         }
       }
-      if (first && slabs > 1) cnt = compact_slab_points<D, false>(ku, N, g, x0, x1, sel, counter);
+      if (first && slabs > 1) cnt = compact_slab_points<D, false>(ku, n_hi, g, x0, x1, sel, counter, n_lo);
       mbar_wait(bar, parity);
       parity ^= 1u;
     } else {
@@ -912,9 +919,10 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
         for (int a2 = 0; a2 < D; ++a2) nk[a2] = __ldg(ku + (size_t)a2 * N + n);
         if (pu) npd = __ldg(pu + n);
       };
-      if (kAheadQ && (int)threadIdx.x < (cnt << lsh)) prefetch(threadIdx.x);
+      const int s_lo = n_lo << lsh, s_hi = n_hi << lsh;                                          // my slots
+      if (kAheadQ && s_lo + (int)threadIdx.x < s_hi) prefetch(s_lo + threadIdx.x);
 #pragma unroll 1
-      for (int slot = threadIdx.x; slot < (cnt << lsh); slot += (int)blockDim.x) {
+      for (int slot = s_lo + threadIdx.x; slot < s_hi; slot += (int)blockDim.x) {
         const unsigned active = __activemask();
         const int n = slot >> lsh, q0 = slot & (lpp - 1);
         if (!kAheadQ) prefetch(slot);
@@ -922,7 +930,7 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
         float kv[D];
 #pragma unroll
         for (int a2 = 0; a2 < D; ++a2) kv[a2] = nk[a2];
-        if (kAheadQ && slot + (int)blockDim.x < (cnt << lsh)) prefetch(slot + (int)blockDim.x);
+        if (kAheadQ && slot + (int)blockDim.x < s_hi) prefetch(slot + (int)blockDim.x);
         const Pos<D> p = point_pos_from_values<D>(kv, g);
         float w[S], gw[S];
         int a[S];
@@ -1030,16 +1038,17 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
     };
     // (only where it fits the 64-register budget of two 512-thread CTAs per SM; the backward modes would spill)
     constexpr bool kAhead = MODE == GATHER_SLICE_FWD;
-    if (kAhead && (int)threadIdx.x < cnt) prefetch(threadIdx.x);
+    const int p_lo = slabs > 1 ? 0 : n_lo, p_hi = slabs > 1 ? cnt : n_hi;                         // my points
+    if (kAhead && p_lo + (int)threadIdx.x < p_hi) prefetch(p_lo + threadIdx.x);
 #pragma unroll 1
-    for (int i = threadIdx.x; i < cnt; i += (int)blockDim.x) {
+    for (int i = p_lo + threadIdx.x; i < p_hi; i += (int)blockDim.x) {
       if (!kAhead) prefetch(i);
       const int n = nn;
       const float pd = npd;
       float kv[D];
 #pragma unroll
       for (int a2 = 0; a2 < D; ++a2) kv[a2] = nk[a2];
-      if (kAhead && i + (int)blockDim.x < cnt) prefetch(i + (int)blockDim.x);
+      if (kAhead && i + (int)blockDim.x < p_hi) prefetch(i + (int)blockDim.x);
       const Pos<D> p = point_pos_from_values<D>(kv, g);
       float w[S];
       int a[S];
@@ -1146,13 +1155,23 @@ cudaError_t launch_gather(const float* keys, const GT* t1, const int* t2, const 
   const Grid<D> g = make_grid<D>(s->size);
   static const bool no_split = getenv("CTB_GATHER_NO_SPLIT") != nullptr;
   const int gsplit = (MODE == GATHER_SLICE_FWD && !no_split) ? (s->F + c.FG - 1) / c.FG : 1;
-  const long long blocks = (long long)s->B * s->H * c.slabs * gsplit;
+  long long blocks = (long long)s->B * s->H * c.slabs * gsplit;
+  // too few work items for 148 SMs x 2 CTAs: split the points of an item over up to 8 CTAs (>= 1024 points each)
+  // as long as a CTA keeps >= 8 corner entries per tile cell (the tile is loaded by every CTA of the item)
+  int psplit = 1;
+  const long long tile_cells = (long long)(c.slabs == 1 ? s->size[0] : c.R + 1) *
+                               (s->dim == 2 ? s->size[1] : s->size[1] * s->size[2]);
+  const long long entries = (long long)s->N << s->dim;
+  while (psplit < 8 && blocks * psplit * 2 <= 2 * 296 && entries / (psplit * 2) >= 8 * tile_cells &&
+         s->N / (psplit * 2) >= 2048)
+    psplit *= 2;
+  blocks *= psplit;
   if (blocks >= (1ll << 31)) return cudaErrorNotSupported;
   cudaError_t e = cudaFuncSetAttribute(tile_gather_kernel<D, MODE, LAYOUT, GT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
   tile_gather_kernel<D, MODE, LAYOUT, GT><<<(unsigned)blocks, tile_threads(), c.smem, stream>>>(
-      keys, t1, t2, in, pad, out, grad_keys, g, s->H, s->F, s->N, c.FG, c.R, c.slabs, c.words, gsplit);
+      keys, t1, t2, in, pad, out, grad_keys, g, s->H, s->F, s->N, c.FG, c.R, c.slabs, c.words, gsplit, psplit);
   return cudaGetLastError();
 }
 
