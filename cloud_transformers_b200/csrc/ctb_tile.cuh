@@ -185,6 +185,16 @@ __device__ __forceinline__ int lds_s32(unsigned addr) {
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+// predicated shared min: one setp + one predicated RED, no branch around the (rare) winner update
+__device__ __forceinline__ void red_shared_min_u32_if(bool p, unsigned addr, unsigned v) {
+  asm volatile(
+      "{\n"
+      " .reg .pred q;\n"
+      " setp.ne.u32 q, %0, 0;\n"
+      " @q red.shared.min.u32 [%1], %2;\n"
+      "}" ::"r"((unsigned)p), "r"(addr), "r"(v)
+      : "memory");
+}
 __device__ __forceinline__ void red_shared_add_u32(unsigned addr, unsigned v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -357,6 +367,7 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   int* targ = (int*)(tval + tw);                                    // max: arg (if any) | sum: high limb
   unsigned short* sel = (unsigned short*)(targ + ((SUM || want_arg) ? tw : 0));
   int* counter = (int*)(sel + ((N + 7) & ~7));                      // [0] compaction, [1] max|v| bits, [2] non-finite
+  const unsigned targ_base = smem_u32(targ);                        // shared-window address (predicated arg reds)
 
   CTB_STAMP_INIT;
   int item = blockIdx.x;
@@ -700,19 +711,32 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
         });
       } else {
         for_channels([&](int f, float ft) {
-          // winners are rare: test all corners branch-free first, take the atomic path only if one matched
-          bool hit[S];
-          bool any = false;
+          if constexpr (D == 2) {
+            // four corners: tile values first (independent loads), then predicated reds for the (rare) winners
+            // (measured: 16^2 F16 0.119 -> 0.109 ms; with eight corners the extra registers spill, 3-D keeps the
+            // test-then-branch form below)
+            int t[S];
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            const int t = ((const int*)tval)[a[s] + f * fs];
-            hit[s] = (__float_as_int(CTB_FMUL(ft, w[s])) == t) & (t != 0);
-            any |= hit[s];
-          }
-          if (any) {
+            for (int s = 0; s < S; ++s) t[s] = ((const int*)tval)[a[s] + f * fs];
 #pragma unroll
             for (int s = 0; s < S; ++s)
-              if (hit[s]) atomicMin((unsigned*)targ + a[s] + f * fs, (unsigned)(s * N + n));
+              red_shared_min_u32_if((__float_as_int(CTB_FMUL(ft, w[s])) == t[s]) & (t[s] != 0),
+                                    targ_base + ((unsigned)(a[s] + f * fs) << 2), (unsigned)(s * N + n));
+          } else {
+            // winners are rare: test all corners branch-free first, take the atomic path only if one matched
+            bool hit[S];
+            bool any = false;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const int t = ((const int*)tval)[a[s] + f * fs];
+              hit[s] = (__float_as_int(CTB_FMUL(ft, w[s])) == t) & (t != 0);
+              any |= hit[s];
+            }
+            if (any) {
+#pragma unroll
+              for (int s = 0; s < S; ++s)
+                if (hit[s]) atomicMin((unsigned*)targ + a[s] + f * fs, (unsigned)(s * N + n));
+            }
           }
         });
       }
