@@ -54,10 +54,13 @@ __device__ unsigned long long g_phase[16];
 #define CTB_STAMP_INIT do { } while (0)
 #endif
 
-constexpr int kTileThreads = 512;   // launch bound; the actual CTA size is blockDim.x (tile_threads())
+#ifndef CTB_TILE_THREADS_DEFAULT
+#define CTB_TILE_THREADS_DEFAULT 512
+#endif
+constexpr int kTileThreads = CTB_TILE_THREADS_DEFAULT;   // launch bound; the actual CTA size is blockDim.x
 inline int tile_threads() {
   static const int t = getenv("CTB_TILE_THREADS") ? atoi(getenv("CTB_TILE_THREADS")) : kTileThreads;
-  return (t == 128 || t == 256 || t == 512) ? t : kTileThreads;
+  return (t >= 128 && t <= kTileThreads && t % 32 == 0) ? t : kTileThreads;
 }
 constexpr int kTileSmemTwoCtas = 110 * 1024;
 constexpr int kTileSmemMax = 220 * 1024;

@@ -23,6 +23,7 @@
 
 namespace ctb {
 
+constexpr int kClThreads = 512; // CTA size of the channel-lane kernel (its staging index math is compile time)
 constexpr int kClChunk = 128;   // points per chunk (power of two)
 
 __host__ __device__ inline int cl_stage_words(int FG) { return (FG * (kClChunk + 1) + 3) & ~3; }
@@ -35,7 +36,7 @@ inline size_t cl_extra_bytes(int FG, int dim, int cells) {          // + per-cel
 }
 
 template <int D, bool SUM, bool PAR, typename GT>
-__global__ void __launch_bounds__(kTileThreads, 2)
+__global__ void __launch_bounds__(kClThreads, 2)
 cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat, const float* __restrict__ pad,
                   GT* __restrict__ z, int* __restrict__ arg, Grid<D> g, int H, int F, int N, int FG, int groups,
                   int tw, int LP) {
@@ -57,12 +58,12 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
   {
     float4* t4 = reinterpret_cast<float4*>(tval);
     int4* a4 = reinterpret_cast<int4*>(targ);
-    for (int i = threadIdx.x; i < (tw >> 2); i += kTileThreads) {
+    for (int i = threadIdx.x; i < (tw >> 2); i += kClThreads) {
       t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (SUM) a4[i] = make_int4(0, 0, 0, 0);
       else if (want_arg) a4[i] = make_int4(-1, -1, -1, -1);
     }
-    if (SUM) for (int i = threadIdx.x; i < g.C; i += kTileThreads) ccnt[i] = 0;
+    if (SUM) for (int i = threadIdx.x; i < g.C; i += kClThreads) ccnt[i] = 0;
     if (threadIdx.x == 0) counter[1] = counter[2] = 0;
   }
   const float* ku = keys + (size_t)unit * D * N;
@@ -77,7 +78,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
   if constexpr (SUM) {
     float m = 0.0f;
     bool bad = false;
-    for (int n = threadIdx.x; n < N; n += kTileThreads) {
+    for (int n = threadIdx.x; n < N; n += kClThreads) {
       const float pd = pu ? __ldg(pu + n) : 1.0f;
       for (int f = 0; f < fg; f += 8) {       // eight independent loads in flight per thread
         float v[8];
@@ -121,7 +122,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
   // Chunk pipeline: while the warps work through chunk c (shared atomics), the features and keys of chunk c+1 are
   // already in flight into registers; they are staged into the other buffer afterwards -- one barrier per chunk
   // and no exposed global-load latency.
-  constexpr int XR = PAR ? (16 * kClChunk / kTileThreads) : (32 * kClChunk / kTileThreads);   // feature regs / thread
+  constexpr int XR = PAR ? (16 * kClChunk / kClThreads) : (32 * kClChunk / kClThreads);   // feature regs / thread
   const int nchunks = (N + kClChunk - 1) / kClChunk;
   float nx[XR], nk[D], npd = 1.0f;          // (the chunk index j of a thread is the same for all its XR rows)
   auto fetch = [&](int c) {                     // global -> registers
@@ -132,7 +133,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
     const bool jok = j < pcn;
 #pragma unroll
     for (int r = 0; r < XR; ++r)
-      nx[r] = (jok && fb + r * (kTileThreads / kClChunk) < fg) ? __ldg(src + (size_t)r * (kTileThreads / kClChunk) * N) : 0.0f;
+      nx[r] = (jok && fb + r * (kClThreads / kClChunk) < fg) ? __ldg(src + (size_t)r * (kClThreads / kClChunk) * N) : 0.0f;
     if (pu) npd = jok ? __ldg(pu + c0 + j) : 0.0f;
     if ((int)threadIdx.x < pcn) {
 #pragma unroll
@@ -147,7 +148,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
     int* pfl = (int*)(pw + kClChunk * S);
 #pragma unroll
     for (int r = 0; r < XR; ++r) {
-      const int i = threadIdx.x + r * kTileThreads;
+      const int i = threadIdx.x + r * kClThreads;
       const int f = i / kClChunk, j = i % kClChunk;
       if (f < fg) xs[f * (kClChunk + 1) + j] = pu ? CTB_FMUL(nx[r], npd) : nx[r];
     }
@@ -181,7 +182,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
       const int* pfl = (const int*)(pw + kClChunk * S);
       // lanes = channels.  A warp step takes the points j, j + LP, j + 2 LP .. so that the staged feature reads of
       // its point groups fall into different banks.
-      for (int it = warp; it < (kClChunk / 32) * LP; it += kTileThreads / 32) {
+      for (int it = warp; it < (kClChunk / 32) * LP; it += kClThreads / 32) {
         const int j = ((it >> lp_sh) << 5) + (it & (LP - 1)) + (sub << lp_sh);
         if (!ch_ok || j >= pcn) continue;
         const float x = xs[ch * (kClChunk + 1) + j];
@@ -258,7 +259,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
   if constexpr (PAR) {
     // pitch 16: lanes along the cells read four channels at a time (16-byte shared loads), stores stay coalesced
     const int C = g.C;
-    for (int i = threadIdx.x; i < C * 4; i += kTileThreads) {
+    for (int i = threadIdx.x; i < C * 4; i += kClThreads) {
       const int r = i % C, qd = i / C;
       if (qd * 4 >= fg) continue;
       const float4 v4 = reinterpret_cast<const float4*>(tval)[r * 4 + qd];
@@ -328,7 +329,7 @@ bool cl_scatter_try(const float* keys, const float* feat, const float* pad, GT* 
   auto launch = [&](auto kernel) {
     *err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (*err != cudaSuccess) return;
-    kernel<<<(unsigned)blocks, kTileThreads, smem, stream>>>(keys, feat, pad, z, arg, g, s->H, s->F, s->N, FG, groups, tw, LP);
+    kernel<<<(unsigned)blocks, kClThreads, smem, stream>>>(keys, feat, pad, z, arg, g, s->H, s->F, s->N, FG, groups, tw, LP);
   };
   if (sum) {
     if (par) launch(cl_scatter_kernel<D, true, true, GT>);
