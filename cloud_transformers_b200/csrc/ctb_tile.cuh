@@ -792,6 +792,27 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
         __stcs(reinterpret_cast<int4*>(au + (size_t)f * g.C) + r,
                reinterpret_cast<const int4*>(targ + (size_t)f * tile_cells)[r]);
     });
+  } else if (LAYOUT == TILE_PM4 && !F32) {
+    // bf16 grid storage, plane-major: four cells per step, rounded to bf16 and stored as 8 bytes
+    if constexpr (!F32) {
+      for_each_plane_element(fg, ncell >> 2, [&](int f, int r) {
+        float4 v4 = reinterpret_cast<const float4*>(tval + (size_t)f * tile_cells)[r];
+        const int4 h4 = (SUM || want_arg) ? reinterpret_cast<const int4*>(targ + (size_t)f * tile_cells)[r]
+                                          : make_int4(0, 0, 0, 0);
+        if (SUM && fixed_point) {
+          v4.x = limbs_to_float(v4.x, h4.x);
+          v4.y = limbs_to_float(v4.y, h4.y);
+          v4.z = limbs_to_float(v4.z, h4.z);
+          v4.w = limbs_to_float(v4.w, h4.w);
+        }
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y), hi = __floats2bfloat162_rn(v4.z, v4.w);
+        uint2 packed;
+        packed.x = *reinterpret_cast<const unsigned*>(&lo);
+        packed.y = *reinterpret_cast<const unsigned*>(&hi);
+        __stcs(reinterpret_cast<uint2*>(zu + (size_t)f * g.C) + r, packed);
+        if (want_arg) __stcs(reinterpret_cast<int4*>(au + (size_t)f * g.C) + r, h4);
+      });
+    }
   } else {
     for_each_plane_element(fg, ncell, [&](int f, int r) {
       float v1 = tval[r * cs + f * fs];
@@ -926,10 +947,33 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
       mbar_wait(bar, parity);
       parity ^= 1u;
     } else {
-      for_each_plane_element(fg, ncell, [&](int f, int r) {
-        s1[r * cs + f * fs] = grid_load(g1 + (size_t)f * g.C + r);
-        if constexpr (MODE == GATHER_SPLAT_BWD) s2[r * cs + f * fs] = __ldcs(g2 + (size_t)f * g.C + r);
-      });
+      bool vec8 = false;
+      if constexpr (LAYOUT == TILE_PM4 && std::is_same<GT, __nv_bfloat16>::value) vec8 = (stride0 & 7) == 0;
+      if (vec8) {
+        // bf16 grid storage, plane-major: 8 cells per 16-byte load, widened to fp32 on the way into the tile
+        if constexpr (std::is_same<GT, __nv_bfloat16>::value) {
+          for_each_plane_element(fg, ncell >> 3, [&](int f, int r) {
+            const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(g1 + (size_t)f * g.C) + r);
+            float4* dst = reinterpret_cast<float4*>(s1 + (size_t)f * tile_cells) + 2 * r;
+            // a bf16 is the high half of the fp32 with the same value
+            dst[0] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                                 __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+            dst[1] = make_float4(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xffff0000u),
+                                 __uint_as_float(raw.w << 16), __uint_as_float(raw.w & 0xffff0000u));
+            if constexpr (MODE == GATHER_SPLAT_BWD) {
+              const int4* src2 = reinterpret_cast<const int4*>(g2 + (size_t)f * g.C) + 2 * r;
+              int4* dst2 = reinterpret_cast<int4*>(s2 + (size_t)f * tile_cells) + 2 * r;
+              dst2[0] = __ldcs(src2);
+              dst2[1] = __ldcs(src2 + 1);
+            }
+          });
+        }
+      } else {
+        for_each_plane_element(fg, ncell, [&](int f, int r) {
+          s1[r * cs + f * fs] = grid_load(g1 + (size_t)f * g.C + r);
+          if constexpr (MODE == GATHER_SPLAT_BWD) s2[r * cs + f * fs] = __ldcs(g2 + (size_t)f * g.C + r);
+        });
+      }
       __syncthreads();
     }
     if constexpr (LAYOUT == TILE_CLQ) {
