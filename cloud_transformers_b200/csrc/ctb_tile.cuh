@@ -183,6 +183,12 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
+// raw bf16 tile element widened to fp32 (a bf16 is the high half of the fp32 with the same value)
+__device__ __forceinline__ float lds_bf16(unsigned addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return __uint_as_float((unsigned)v << 16);
+}
 __device__ __forceinline__ int lds_s32(unsigned addr) {
   int v;
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -844,9 +850,10 @@ cudaError_t launch_tile_scatter(const float* keys, const float* feat, const floa
   return cudaGetLastError();
 }
 
-inline int effective_layout(int layout, const void* p1, const void* p2) {
+inline int effective_layout(int layout, const void* p1, const void* p2, bool raw16 = false, int stride0 = 0) {
   if (layout == TILE_PM4 && (((reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2)) & 15) != 0))
     return TILE_PM1;
+  if (layout == TILE_PM4 && raw16 && (stride0 % 8) != 0) return TILE_PM1;   // bf16 rows must be 16-byte multiples
   return layout;
 }
 
@@ -889,7 +896,12 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
   // keep gsplit == 1 because one thread accumulates grad_keys over the groups in a fixed order.
   constexpr int S = 1 << D;
   constexpr bool CL = LAYOUT == TILE_CL || LAYOUT == TILE_CLQ;
-  constexpr bool TMA = LAYOUT == TILE_PM4 && std::is_same<GT, float>::value;   // raw tile copy by the copy engine
+  // plane-major tiles arrive as raw copies by the copy engine: fp32 grids as they are, bf16 grids (RAW16) stay bf16
+  // in shared memory and are widened when a corner is read (the host only picks PM4 for bf16 if rows are 16-byte
+  // multiples, see effective_layout)
+  constexpr bool RAW16 = LAYOUT == TILE_PM4 && std::is_same<GT, __nv_bfloat16>::value;
+  constexpr bool TMA = LAYOUT == TILE_PM4;
+  constexpr unsigned ESH = RAW16 ? 1u : 2u;       // log2 of the tile element size of s1
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int stride0 = g.stride[0];
   const int W0 = g.W[0];
@@ -935,45 +947,22 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
     if constexpr (TMA) {
       // one thread hands the whole tile to the copy engine; the CTA compacts its points meanwhile
       if (threadIdx.x == 0) {
-        const uint32_t plane_bytes = (uint32_t)ncell * 4u;
-        mbar_expect_tx(bar, plane_bytes * fg * (MODE == GATHER_SPLAT_BWD ? 2u : 1u));
+        const uint32_t plane_bytes = (uint32_t)ncell << ESH, arg_bytes = (uint32_t)ncell * 4u;
+        mbar_expect_tx(bar, (plane_bytes + (MODE == GATHER_SPLAT_BWD ? arg_bytes : 0u)) * fg);
         for (int f = 0; f < fg; ++f) {
-          bulk_g2s(s1 + (size_t)f * tile_cells, (const float*)g1 + (size_t)f * g.C, plane_bytes, bar);
+          bulk_g2s((unsigned char*)s1 + (((size_t)f * tile_cells) << ESH), g1 + (size_t)f * g.C, plane_bytes, bar);
           if constexpr (MODE == GATHER_SPLAT_BWD)
-            bulk_g2s(s2 + (size_t)f * tile_cells, g2 + (size_t)f * g.C, plane_bytes, bar);
+            bulk_g2s(s2 + (size_t)f * tile_cells, g2 + (size_t)f * g.C, arg_bytes, bar);
         }
       }
       if (first && slabs > 1) cnt = compact_slab_points<D, false>(ku, n_hi, g, x0, x1, sel, counter, n_lo);
       mbar_wait(bar, parity);
       parity ^= 1u;
     } else {
-      bool vec8 = false;
-      if constexpr (LAYOUT == TILE_PM4 && std::is_same<GT, __nv_bfloat16>::value) vec8 = (stride0 & 7) == 0;
-      if (vec8) {
-        // bf16 grid storage, plane-major: 8 cells per 16-byte load, widened to fp32 on the way into the tile
-        if constexpr (std::is_same<GT, __nv_bfloat16>::value) {
-          for_each_plane_element(fg, ncell >> 3, [&](int f, int r) {
-            const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(g1 + (size_t)f * g.C) + r);
-            float4* dst = reinterpret_cast<float4*>(s1 + (size_t)f * tile_cells) + 2 * r;
-            // a bf16 is the high half of the fp32 with the same value
-            dst[0] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
-                                 __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
-            dst[1] = make_float4(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xffff0000u),
-                                 __uint_as_float(raw.w << 16), __uint_as_float(raw.w & 0xffff0000u));
-            if constexpr (MODE == GATHER_SPLAT_BWD) {
-              const int4* src2 = reinterpret_cast<const int4*>(g2 + (size_t)f * g.C) + 2 * r;
-              int4* dst2 = reinterpret_cast<int4*>(s2 + (size_t)f * tile_cells) + 2 * r;
-              dst2[0] = __ldcs(src2);
-              dst2[1] = __ldcs(src2 + 1);
-            }
-          });
-        }
-      } else {
-        for_each_plane_element(fg, ncell, [&](int f, int r) {
-          s1[r * cs + f * fs] = grid_load(g1 + (size_t)f * g.C + r);
-          if constexpr (MODE == GATHER_SPLAT_BWD) s2[r * cs + f * fs] = __ldcs(g2 + (size_t)f * g.C + r);
-        });
-      }
+      for_each_plane_element(fg, ncell, [&](int f, int r) {
+        s1[r * cs + f * fs] = grid_load(g1 + (size_t)f * g.C + r);
+        if constexpr (MODE == GATHER_SPLAT_BWD) s2[r * cs + f * fs] = __ldcs(g2 + (size_t)f * g.C + r);
+      });
       __syncthreads();
     }
     if constexpr (LAYOUT == TILE_CLQ) {
@@ -1135,15 +1124,19 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
       // byte addresses of the point's corner cells in the shared window; channel f adds f * fstep
       unsigned ab[S];
 #pragma unroll
-      for (int s = 0; s < S; ++s) ab[s] = s1_base + ((unsigned)a[s] << 2);
-      const unsigned fstep = (unsigned)fs << 2;
+      for (int s = 0; s < S; ++s) ab[s] = s1_base + ((unsigned)a[s] << ESH);
+      const unsigned fstep = (unsigned)fs << ESH;
+      auto tile_val = [&](unsigned addr) {
+        if constexpr (RAW16) return lds_bf16(addr);
+        else return lds_f32(addr);
+      };
       if constexpr (MODE == GATHER_SLICE_FWD) {
 #pragma unroll 4
         for (int f = 0; f < fg; ++f) {
           const unsigned off = (unsigned)f * fstep;
-          float acc = CTB_FMUL(lds_f32(ab[0] + off), w[0]);
+          float acc = CTB_FMUL(tile_val(ab[0] + off), w[0]);
 #pragma unroll
-          for (int s = 1; s < S; ++s) acc = fmaf(lds_f32(ab[s] + off), w[s], acc);
+          for (int s = 1; s < S; ++s) acc = fmaf(tile_val(ab[s] + off), w[s], acc);
           if (pu) acc = CTB_FMUL(acc, pd);
           out[po + (size_t)f * N] = acc;
         }
@@ -1164,7 +1157,7 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
             if (f + q < fg) {
               const unsigned off = (unsigned)(f + q) * fstep;
 #pragma unroll
-              for (int s = 0; s < S; ++s) gw[s] = fmaf(lds_f32(ab[s] + off), gc[q], gw[s]);
+              for (int s = 0; s < S; ++s) gw[s] = fmaf(tile_val(ab[s] + off), gc[q], gw[s]);
             }
           }
         }
@@ -1188,9 +1181,11 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
 #pragma unroll
               for (int s = 0; s < S; ++s) {
                 const unsigned ad = ab[s] + off;
-                const bool win = lds_s32(ad + s12) == s * N + n;
+                // arg is an int32 tile behind s1: same element index, 4-byte elements
+                const unsigned arg_ad = RAW16 ? s1_base + s12 + ((ad - s1_base) << 1) : ad + s12;
+                const bool win = lds_s32(arg_ad) == s * N + n;
                 float gz = 0.0f;
-                if (win) gz = lds_f32(ad);
+                if (win) gz = tile_val(ad);
                 gf = fmaf(gz, w[s], gf);
                 gw[s] = fmaf(gz, fc[q], gw[s]);
               }
@@ -1251,7 +1246,8 @@ cudaError_t tile_gather(const float* keys, const GT* t1, const int* t2, const fl
                         float* out, float* grad_keys, const ctb_shape* s, cudaStream_t stream) {
   TileConfig c;
   if (!gather_config(s, MODE, &c)) return cudaErrorNotSupported;
-  switch (effective_layout(c.layout, t1, t2)) {
+  const int stride0 = s->dim == 2 ? s->size[1] : s->size[1] * s->size[2];
+  switch (effective_layout(c.layout, t1, t2, std::is_same<GT, __nv_bfloat16>::value, stride0)) {
     case TILE_PM4: return launch_gather<D, MODE, TILE_PM4, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
     case TILE_PM1: return launch_gather<D, MODE, TILE_PM1, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
     case TILE_CLQ: return launch_gather<D, MODE, TILE_CLQ, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
