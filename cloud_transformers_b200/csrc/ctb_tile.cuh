@@ -227,7 +227,11 @@ inline int tile_array_words(int cells, int FG, int layout) {
 //                                              their features are read with gaps
 // Whole-grid groups win as soon as a group holds >= 3 channels (or all of them); otherwise all channels in
 // balanced slabs of >= 3 rows; otherwise fewer channels in slabs.  halo = 1 for gathers (the +1 corner row).
-inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* out, bool allow_quad = false) {
+inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* out, bool allow_quad = false,
+                        int cell_bytes = 0) {
+  // cell_bytes: shared-memory bytes per (cell, channel) over all tile arrays; default 4 per array.  The gathers of
+  // the bf16 storage mode keep the grid tile as raw bf16: 2 bytes (+ 4 for the int32 arg tile of Splat backward).
+  if (cell_bytes == 0) cell_bytes = 4 * arrays;
   const int stride0 = s->dim == 2 ? s->size[1] : s->size[1] * s->size[2];
   const int W0 = s->size[0];
   const long long C = (long long)W0 * stride0;
@@ -240,7 +244,7 @@ inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* ou
   if (allow_quad && dense && s->F % 4 == 0 && s->F >= 8) {
     const size_t lb = (((size_t)s->N + 7) & ~(size_t)7) * 2 + 32;
     for (int FG = s->F; FG >= 8; FG -= 4) {
-      const size_t b = (size_t)tile_array_words((int)C, FG, TILE_CLQ) * 4 * arrays + lb;
+      const size_t b = (size_t)tile_array_words((int)C, FG, TILE_CLQ) * cell_bytes + lb;
       if (b <= (size_t)kTileSmemTwoCtas) {
         const int groups = (s->F + FG - 1) / FG;
         FG = ((s->F + groups - 1) / groups + 3) & ~3;     // balanced groups, still multiples of 4
@@ -249,7 +253,7 @@ inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* ou
         out->slabs = 1;
         out->layout = TILE_CLQ;
         out->words = tile_array_words((int)C, FG, TILE_CLQ);
-        out->smem = (size_t)out->words * 4 * arrays + lb;
+        out->smem = (size_t)out->words * cell_bytes + lb;
         return true;
       }
     }
@@ -257,7 +261,7 @@ inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* ou
   const int layout = dense ? TILE_CL : ((stride0 % 4 == 0) ? TILE_PM4 : TILE_PM1);
   const size_t list_bytes = (((size_t)s->N + 7) & ~(size_t)7) * 2 + 32;  // uint16 list + counters + mbarrier
   auto bytes = [&](long long cells, int FG) {
-    return (size_t)tile_array_words((int)cells, FG, layout) * 4 * arrays + list_bytes;
+    return (size_t)tile_array_words((int)cells, FG, layout) * cell_bytes + list_bytes;
   };
   auto fill = [&](int FG, int R, int slabs) {
     out->FG = FG;
@@ -265,7 +269,7 @@ inline bool tile_config(const ctb_shape* s, int arrays, int halo, TileConfig* ou
     out->slabs = slabs;
     out->layout = layout;
     out->words = tile_array_words((slabs == 1 ? W0 : R + halo) * stride0, FG, layout);
-    out->smem = (size_t)out->words * 4 * arrays + list_bytes;
+    out->smem = (size_t)out->words * cell_bytes + list_bytes;
   };
   // tuning knobs for experiments (not part of the ABI): CTB_TILE_BUDGET_KB, CTB_TILE_MIN_GROUP
   static const int env_budget = getenv("CTB_TILE_BUDGET_KB") ? atoi(getenv("CTB_TILE_BUDGET_KB")) : 0;
@@ -909,8 +913,8 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
   const int cs = CL ? cl_pitch(FG, LAYOUT) : 1;
   const int fs = CL ? 1 : tile_cells;
   float* s1 = (float*)smem_raw;
-  int* s2 = (int*)(s1 + tw);                                        // (SPLAT_BWD: arg)
-  const unsigned s1_base = smem_u32(s1), s12 = (unsigned)tw << 2;   // shared-window address of s1; byte distance to s2
+  int* s2 = (int*)((unsigned char*)s1 + ((size_t)tw << ESH));       // (SPLAT_BWD: arg) behind the tw elements of s1
+  const unsigned s1_base = smem_u32(s1), s12 = (unsigned)tw << ESH; // shared-window address of s1; byte distance to s2
   unsigned short* sel = (unsigned short*)(s2 + (MODE == GATHER_SPLAT_BWD ? tw : 0));
   int* counter = (int*)(sel + ((N + 7) & ~7));
   uint64_t* bar = (uint64_t*)(counter + 4);     // 16-byte aligned: the list is padded to 8 entries
@@ -1210,9 +1214,19 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
   }
 }
 
-inline bool gather_config(const ctb_shape* s, int mode, TileConfig* out) {
+inline bool gather_config(const ctb_shape* s, int mode, TileConfig* out, bool aligned16 = true) {
   // quad lanes measured faster only for the 3-D Slice forward (c3d 0.16 -> 0.13 ms)
-  return tile_config(s, mode == GATHER_SPLAT_BWD ? 2 : 1, 1, out, mode == GATHER_SLICE_FWD && s->dim == 3);
+  const int arrays = mode == GATHER_SPLAT_BWD ? 2 : 1;
+  const bool quad = mode == GATHER_SLICE_FWD && s->dim == 3;
+  if (!tile_config(s, arrays, 1, out, quad)) return false;
+  // bf16 storage, plane-major, rows that are 16-byte multiples: the tile stays raw bf16 (see tile_gather_kernel),
+  // so the same budget holds twice the rows
+  const int stride0 = s->dim == 2 ? s->size[1] : s->size[1] * s->size[2];
+  if (s->grid_dtype == CTB_DTYPE_BF16 && out->layout == TILE_PM4 && aligned16 && stride0 % 8 == 0) {
+    TileConfig c2;
+    if (tile_config(s, arrays, 1, &c2, quad, mode == GATHER_SPLAT_BWD ? 6 : 2) && c2.layout == TILE_PM4) *out = c2;
+  }
+  return true;
 }
 
 template <int D, int MODE, int LAYOUT, typename GT>
@@ -1245,7 +1259,8 @@ template <int D, int MODE, typename GT>
 cudaError_t tile_gather(const float* keys, const GT* t1, const int* t2, const float* in, const float* pad,
                         float* out, float* grad_keys, const ctb_shape* s, cudaStream_t stream) {
   TileConfig c;
-  if (!gather_config(s, MODE, &c)) return cudaErrorNotSupported;
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(t1) | reinterpret_cast<uintptr_t>(t2)) & 15) == 0;
+  if (!gather_config(s, MODE, &c, aligned16)) return cudaErrorNotSupported;
   const int stride0 = s->dim == 2 ? s->size[1] : s->size[1] * s->size[2];
   switch (effective_layout(c.layout, t1, t2, std::is_same<GT, __nv_bfloat16>::value, stride0)) {
     case TILE_PM4: return launch_gather<D, MODE, TILE_PM4, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
