@@ -224,6 +224,37 @@ def run_ours(args):
     top = max(ops, key=lambda o: o["ms"])
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- context: the same step with the grids stored as bf16 (fp32 arithmetic; tolerance rel 1e-2, not the headline)
+    bf16_mode = None
+    if args.grid_dtype == "f32" and rank == 0:
+        try:
+            g2 = torch.Generator(device=dev).manual_seed(43)
+            d16, p16 = {}, {}
+            for name, dim, W, F in CLASSES:
+                d16[name] = make_class_inputs(g2, dim, W, F, B, dev, torch.bfloat16)
+                p16[name] = HotPath(W, H, dim, B, F, N_PTS, dev, mode=args.mode, grid_dtype=torch.bfloat16)
+
+            def step16():
+                for name, dim, W, F in order:
+                    p16[name].fwd_bwd(*d16[name])
+
+            step16()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                step16()
+            b.record()
+            torch.cuda.synchronize()
+            ms16 = a.elapsed_time(b) / 3
+            bytes16 = sum(algorithmic_bytes(N_PTS, dim, F, W ** dim, e_grid=2)["total"] * B * H for _, dim, W, F in order)
+            bf16_mode = {"value": round(pt_heads_step / (ms16 * 1e-3) / 1e9, 4), "unit": UNIT, "ms_per_step": round(ms16, 3),
+                         "algorithmic_gbs": round(bytes16 / (ms16 * 1e-3) / 1e9, 1),
+                         "what": "grids (z, convolved, grad_grid, grad_z) stored as bf16, fp32 arithmetic, this rank only"}
+            del d16, p16
+        except Exception as exc:  # noqa: BLE001
+            bf16_mode = {"unavailable": repr(exc)[:200]}
+
     # ---- e2e through the public modules with host buffers -----------------------------------------
     e2e = run_e2e(args, dev, world, rank, data, order)
     ref_gpu = reference_composition_on_gpu(dev, data) if rank == 0 else None
@@ -256,6 +287,7 @@ def run_ours(args):
             "clocks": clocks,
             "cpu_baseline": cpu,
             "reference_composition_gpu": ref_gpu,
+            "bf16_grid_mode": bf16_mode,
         }
         print(json.dumps(line))
     if world > 1:
