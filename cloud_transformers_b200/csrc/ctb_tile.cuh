@@ -57,6 +57,9 @@ __device__ unsigned long long g_phase[16];
 #ifndef CTB_TILE_THREADS_DEFAULT
 #define CTB_TILE_THREADS_DEFAULT 512
 #endif
+#ifndef CTB_TILE_MIN_CTAS
+#define CTB_TILE_MIN_CTAS 2
+#endif
 constexpr int kTileThreads = CTB_TILE_THREADS_DEFAULT;   // launch bound; the actual CTA size is blockDim.x
 inline int tile_threads() {
   static const int t = getenv("CTB_TILE_THREADS") ? atoi(getenv("CTB_TILE_THREADS")) : kTileThreads;
@@ -362,7 +365,7 @@ __device__ __forceinline__ void for_each_plane_element(int fg, int count, Fn fn)
 
 // ------------------------------------------------------------------------------------------------------
 template <int D, bool SUM, int LAYOUT, typename GT>
-__global__ void __launch_bounds__(kTileThreads, 2)
+__global__ void __launch_bounds__(kTileThreads, CTB_TILE_MIN_CTAS)
 tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat, const float* __restrict__ pad,
                     GT* __restrict__ z, int* __restrict__ arg, Grid<D> g, int H, int F, int N, int FG, int R,
                     int slabs, int groups, int tw) {
@@ -888,7 +891,7 @@ enum GatherMode { GATHER_SLICE_FWD = 0, GATHER_SLICE_BWD_KEYS = 1, GATHER_SPLAT_
 // One CTA = (unit, slab).  Loops over channel groups; every point is resolved in the single slab that holds
 // its base row, so grad_keys needs no cross-CTA reduction.
 template <int D, int MODE, int LAYOUT, typename GT>
-__global__ void __launch_bounds__(kTileThreads, 2)
+__global__ void __launch_bounds__(kTileThreads, CTB_TILE_MIN_CTAS)
 tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, const int* __restrict__ t2,
                    const float* __restrict__ in, const float* __restrict__ pad, float* __restrict__ out,
                    float* __restrict__ grad_keys, Grid<D> g, int H, int F, int N, int FG, int R, int slabs, int tw,
