@@ -497,6 +497,8 @@ BIG = [
     (3, 64, 4, 4, 32768, 1),      # sweep: 3D 64^3 (one channel plane = 1 MB > shared memory => row slabs)
     (2, 32, 64, 32, 1024, 1),     # sweep: 64 heads, F = 32
     (2, 256, 2, 4, 262144, 1),    # sweep max: N = 256K (beyond the tile kernels => L2-atomic kernels)
+    (2, 16, 2, 16, 8192, 1),      # 2 units only: the gathers split a unit's points over 4 CTAs (channel-last tile)
+    (3, 16, 2, 16, 16384, 1),     # same with plane-major TMA tiles and several channel groups
 ]
 
 
