@@ -82,6 +82,11 @@ class DifferentiablePositions(DifferentiableGridModule):
                  flattened_index  int64   [batch_size, heads, 2^dim, num_points]
         '''
         assert keys.size(1) == self.heads * self.dim
+        if keys.numel() == 0:
+            # empty batch / empty cloud: the reference's elementwise ops return empty tensors of these shapes
+            B, N, S = keys.size(0), keys.size(2), 2 ** self.dim
+            return (keys.new_zeros((B, self.heads, S, N)) + 0.0 * keys.sum(),
+                    torch.zeros((B, self.heads, S, N), dtype=torch.int64, device=keys.device))
         local_coordinate, flattened_index = CF.positions(keys, self._geom)
         tag = (CF.PositionsHandle(keys, self._geom), local_coordinate._version, flattened_index._version)
         local_coordinate._ctb_tag = tag
@@ -106,6 +111,10 @@ class Splat(DifferentiableGridModule):
         '''
         assert features.dtype == torch.float32
         assert features.size(1) % self.heads == 0
+        if features.numel() == 0:
+            # nothing to splat: scatter_max leaves its zero-initialised output untouched (cloud_transform.py:164-173)
+            z = features.new_zeros((features.size(0), features.size(1)) + tuple(self._geom.sizes)) + 0.0 * features.sum()
+            return z if self.out_dtype is None else z.to(self.out_dtype)
         reduce = _lib.REDUCE_MAX if self.reduce == "max" else _lib.REDUCE_SUM
         handle = _handle_of(local_coordinate, flattened_index)
         if handle is not None and handle.geom.sizes == self._geom.sizes and handle.geom.heads == self.heads:
@@ -122,6 +131,10 @@ class Slice(DifferentiableGridModule):
         :return: sliced features float32 [batch_size, heads * feature_dim, num_points]
         '''
         assert convolved.size(1) % self.heads == 0
+        if local_coordinate.numel() == 0 or convolved.numel() == 0:
+            # no points: torch.gather on an empty index returns an empty tensor (cloud_transform.py:216-221)
+            out = convolved.new_zeros((convolved.size(0), convolved.size(1), local_coordinate.size(-1)), dtype=torch.float32)
+            return out + 0.0 * convolved.float().sum()
         handle = _handle_of(local_coordinate, flattened_index)
         if handle is not None and handle.geom.sizes == self._geom.sizes and handle.geom.heads == self.heads:
             return CF.fused_slice(handle, convolved, pts_padding)

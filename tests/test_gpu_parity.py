@@ -402,6 +402,28 @@ def test_tile_sum_limb_headroom_worst_case():
             assert np.array_equal(z, want), (dim, W, F, sign, float(np.abs(z - want).max()))
 
 
+def test_empty_cloud_matches_reference_shapes():
+    """N = 0 (and B = 0): the reference's torch ops return a zero grid / empty per-point tensors; so does the mirror,
+    and gradients flow (as zeros) instead of raising."""
+    for B, N in ((2, 0), (0, 5)):
+        H, dim, W, F = 2, 3, 4, 3
+        dp = ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim)
+        sp = ctb.Splat(tensor_size=W, heads=H, dim=dim)
+        sl = ctb.Slice(tensor_size=W, heads=H, dim=dim)
+        keys = torch.zeros(B, H * dim, N, device=DEV, requires_grad=True)
+        feat = torch.zeros(B, H * F, N, device=DEV, requires_grad=True)
+        lc, idx = dp(keys)
+        assert lc.shape == (B, H, 8, N) and idx.shape == (B, H, 8, N) and idx.dtype == torch.int64
+        z = sp(lc, idx, feat)
+        assert z.shape == (B, H * F, W, W, W) and float(z.abs().sum()) == 0.0
+        conv = torch.randn(B, H * F, W, W, W, device=DEV, requires_grad=True)
+        out = sl(lc, idx, conv)
+        assert out.shape == (B, H * F, N)
+        (z.sum() + out.sum()).backward()
+        assert feat.grad is not None and feat.grad.shape == feat.shape
+        assert conv.grad is not None and float(conv.grad.abs().sum()) == 0.0
+
+
 # --- A8: fused projection + tanh, and the MHCT block mirror ------------------------------------------
 def _torch_keys(pcd, keys_res, shift, log_R, scales, res_scale, H, dim):
     """layers/utils.py:25-34 / :53-61 + multihead_ct.py:93-97 in plain torch."""
@@ -538,7 +560,8 @@ def test_large_shapes_all_algorithms_agree(shape):
 
 # --- bf16 grid storage mode (north star: rel 1e-2) -----------------------------------------------------
 @pytest.mark.parametrize("shape", [(2, 128, 4, 4, 2048, 2), (3, 32, 4, 4, 2048, 1), (2, 64, 4, 16, 2048, 1),
-                                   (3, 8, 4, 32, 2048, 1), (2, (24, 40), 3, 5, 777, 2)],
+                                   (3, 8, 4, 32, 2048, 1), (2, (24, 40), 3, 5, 777, 2), (2, (10, 12), 2, 3, 500, 1),
+                                   (3, 16, 2, 16, 16384, 1)],
                          ids=lambda s: "d%d_w%s_h%d_f%d_n%d_b%d" % s)
 def test_bf16_grid_storage_mode(shape):
     """Grids (z, convolved, grad_grid, grad_z) stored as bf16, arithmetic in fp32: against the fp32 oracle fed with the
