@@ -10,7 +10,11 @@
 //   A. all threads: features of the chunk -> shared [fg][chunk+1] with coalesced loads (the transpose that
 //      turns "lane = point" loads into "lane = channel" reads), positions of the chunk (lane = point) -> shared
 //   B. every warp walks points of the chunk, lanes = channels (32 / LP points at a time for LP-lane groups)
-// Arithmetic and results are identical to tile_scatter_kernel (same products, integer max / min / add).
+// The chunks are double-buffered: while B runs on chunk c, the global loads of chunk c+1 are in flight into
+// registers and are staged into the other buffer afterwards (one barrier per chunk).
+// Arithmetic and results are identical to tile_scatter_kernel (same products, integer max / min / add); the sum
+// adds the RAW limb words (rounding constant included) and a per-cell contribution count removes the constant at
+// read-out, which saves two integer instructions per element.
 //
 // Paired mode (PAR: groups of 9..16 channels, last grid axis even).  Two points share a warp step, 16 lanes each.
 // The cell pitch is 16 words, so a cell lives in banks 0-15 (even cell) or 16-31 (odd cell), and the parity of a
