@@ -187,13 +187,13 @@ inline cudaError_t scatter_dispatch(const float* keys, const float* feat, const 
 
 template <int MODE>
 cudaError_t gather_dispatch(const float* keys, const void* t1, const int* t2, const float* in, const float* pad,
-                            float* out, float* grad_keys, const ctb_shape* s, cudaStream_t st) {
+                            float* out, float* grad_keys, const ctb_shape* s, cudaStream_t st, bool overlap_prev = false) {
   const bool bf = s->grid_dtype == CTB_DTYPE_BF16;
   if (s->dim == 2)
-    return bf ? ctb::tile_gather<2, MODE, bf16_t>(keys, (const bf16_t*)t1, t2, in, pad, out, grad_keys, s, st)
-              : ctb::tile_gather<2, MODE, float>(keys, (const float*)t1, t2, in, pad, out, grad_keys, s, st);
-  return bf ? ctb::tile_gather<3, MODE, bf16_t>(keys, (const bf16_t*)t1, t2, in, pad, out, grad_keys, s, st)
-            : ctb::tile_gather<3, MODE, float>(keys, (const float*)t1, t2, in, pad, out, grad_keys, s, st);
+    return bf ? ctb::tile_gather<2, MODE, bf16_t>(keys, (const bf16_t*)t1, t2, in, pad, out, grad_keys, s, st, overlap_prev)
+              : ctb::tile_gather<2, MODE, float>(keys, (const float*)t1, t2, in, pad, out, grad_keys, s, st, overlap_prev);
+  return bf ? ctb::tile_gather<3, MODE, bf16_t>(keys, (const bf16_t*)t1, t2, in, pad, out, grad_keys, s, st, overlap_prev)
+            : ctb::tile_gather<3, MODE, float>(keys, (const float*)t1, t2, in, pad, out, grad_keys, s, st, overlap_prev);
 }
 
 #define CTB_DISPATCH_DIM(shape, call2, call3) ((shape)->dim == 2 ? (call2) : (call3))
@@ -424,9 +424,11 @@ int ctb_slice_bwd_keys(const float* keys, const void* grid_any, const float* pad
       st = cuda_status(scatter_dispatch(keys, grad_out, pad, grad_grid_any, nullptr, shape, true, (cudaStream_t)stream));
     }
     if (st) return st;
-    // ... and grad_keys: tile gather against the convolved grid.
+    // ... and grad_keys: tile gather against the convolved grid.  It reads keys / grid / grad_out and writes
+    // grad_keys only -- nothing the scatter above touches -- so in TILE mode it may overlap the scatter's last wave.
     return cuda_status(gather_dispatch<ctb::GATHER_SLICE_BWD_KEYS>(keys, grid_any, nullptr, grad_out, pad, nullptr,
-                                                                    grad_keys, shape, (cudaStream_t)stream));
+                                                                    grad_keys, shape, (cudaStream_t)stream,
+                                                                    mode == CTB_MODE_TILE));
   }
   if (shape->grid_dtype != CTB_DTYPE_F32) return CTB_ERR_UNSUPPORTED;
   if (mode != CTB_MODE_ATOMIC) return CTB_ERR_INVALID_ARGUMENT;

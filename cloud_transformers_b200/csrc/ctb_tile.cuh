@@ -386,6 +386,9 @@ tile_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ fe
   const unsigned targ_base = smem_u32(targ);                        // shared-window address (predicated arg reds)
 
   CTB_STAMP_INIT;
+  // a kernel launched behind this one with programmatic stream serialization (the key-gradient gather of Slice
+  // backward, which reads nothing written here) may start filling the SMs this grid's last wave leaves idle
+  asm volatile("griddepcontrol.launch_dependents;");
   int item = blockIdx.x;
   const int slab = item % slabs;
   item /= slabs;
@@ -1234,7 +1237,8 @@ inline bool gather_config(const ctb_shape* s, int mode, TileConfig* out, bool al
 
 template <int D, int MODE, int LAYOUT, typename GT>
 cudaError_t launch_gather(const float* keys, const GT* t1, const int* t2, const float* in, const float* pad,
-                          float* out, float* grad_keys, const ctb_shape* s, const TileConfig& c, cudaStream_t stream) {
+                          float* out, float* grad_keys, const ctb_shape* s, const TileConfig& c, cudaStream_t stream,
+                          bool overlap_prev) {
   const Grid<D> g = make_grid<D>(s->size);
   static const bool no_split = getenv("CTB_GATHER_NO_SPLIT") != nullptr;
   const int gsplit = (MODE == GATHER_SLICE_FWD && !no_split) ? (s->F + c.FG - 1) / c.FG : 1;
@@ -1253,6 +1257,24 @@ cudaError_t launch_gather(const float* keys, const GT* t1, const int* t2, const 
   cudaError_t e = cudaFuncSetAttribute(tile_gather_kernel<D, MODE, LAYOUT, GT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
+  static const bool no_pdl = getenv("CTB_NO_PDL") != nullptr;
+  if (overlap_prev && !no_pdl) {
+    // Programmatic dependent launch: this grid does not consume anything the previous kernel on the stream writes
+    // (the caller vouches for that), so its CTAs may start as soon as the previous grid's last wave is resident
+    // (that kernel signals griddepcontrol.launch_dependents at its start) and fill the tail of its last wave.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3((unsigned)tile_threads());
+    cfg.dynamicSmemBytes = c.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tile_gather_kernel<D, MODE, LAYOUT, GT>, keys, t1, t2, in, pad, out, grad_keys, g, s->H,
+                              s->F, s->N, c.FG, c.R, c.slabs, c.words, gsplit, psplit);
+  }
   tile_gather_kernel<D, MODE, LAYOUT, GT><<<(unsigned)blocks, tile_threads(), c.smem, stream>>>(
       keys, t1, t2, in, pad, out, grad_keys, g, s->H, s->F, s->N, c.FG, c.R, c.slabs, c.words, gsplit, psplit);
   return cudaGetLastError();
@@ -1260,16 +1282,16 @@ cudaError_t launch_gather(const float* keys, const GT* t1, const int* t2, const 
 
 template <int D, int MODE, typename GT>
 cudaError_t tile_gather(const float* keys, const GT* t1, const int* t2, const float* in, const float* pad,
-                        float* out, float* grad_keys, const ctb_shape* s, cudaStream_t stream) {
+                        float* out, float* grad_keys, const ctb_shape* s, cudaStream_t stream, bool overlap_prev = false) {
   TileConfig c;
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(t1) | reinterpret_cast<uintptr_t>(t2)) & 15) == 0;
   if (!gather_config(s, MODE, &c, aligned16)) return cudaErrorNotSupported;
   const int stride0 = s->dim == 2 ? s->size[1] : s->size[1] * s->size[2];
   switch (effective_layout(c.layout, t1, t2, std::is_same<GT, __nv_bfloat16>::value, stride0)) {
-    case TILE_PM4: return launch_gather<D, MODE, TILE_PM4, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
-    case TILE_PM1: return launch_gather<D, MODE, TILE_PM1, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
-    case TILE_CLQ: return launch_gather<D, MODE, TILE_CLQ, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
-    default: return launch_gather<D, MODE, TILE_CL, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream);
+    case TILE_PM4: return launch_gather<D, MODE, TILE_PM4, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream, overlap_prev);
+    case TILE_PM1: return launch_gather<D, MODE, TILE_PM1, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream, overlap_prev);
+    case TILE_CLQ: return launch_gather<D, MODE, TILE_CLQ, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream, overlap_prev);
+    default: return launch_gather<D, MODE, TILE_CL, GT>(keys, t1, t2, in, pad, out, grad_keys, s, c, stream, overlap_prev);
   }
 }
 

@@ -56,6 +56,7 @@ cl_scatter_kernel(const float* __restrict__ keys, const float* __restrict__ feat
   int* counter = (int*)(stage + 2 * bw);                             // [1] max|v| bits, [2] non-finite
   int* ccnt = counter + 4;                                           // sum: contributions per cell
 
+  asm volatile("griddepcontrol.launch_dependents;");   // see tile_scatter_kernel
   const int f0 = (blockIdx.x % groups) * FG;
   const int unit = blockIdx.x / groups;
   const int fg = min(FG, F - f0);
