@@ -4,9 +4,10 @@
 #include "../../include/ctb200.h"
 #include "ctb_positions.cuh"
 #include "ctb_generic.cuh"
-#include "ctb_sorted.cuh"
+#include "ctb_plan.cuh"
 #include "ctb_tile.cuh"
 #include "ctb_tile_cl.cuh"
+#include "ctb_binned.cuh"
 #include "ctb_project.cuh"
 
 namespace {
@@ -196,6 +197,32 @@ cudaError_t gather_dispatch(const float* keys, const void* t1, const int* t2, co
             : ctb::tile_gather<3, MODE, float>(keys, (const float*)t1, t2, in, pad, out, grad_keys, s, st, overlap_prev);
 }
 
+// binned (output-stationary) scatter over the plan's entry lists: reduce x grid-dtype dispatch
+inline cudaError_t binned_dispatch(const float* feat, const float* pad, const void* plan, void* z, int* arg,
+                                   const ctb_shape* s, bool sum, cudaStream_t st) {
+  const bool bf = s->grid_dtype == CTB_DTYPE_BF16;
+  if (sum)
+    return bf ? ctb::bin_scatter<true, bf16_t>(feat, pad, plan, (bf16_t*)z, arg, s, st)
+              : ctb::bin_scatter<true, float>(feat, pad, plan, (float*)z, arg, s, st);
+  return bf ? ctb::bin_scatter<false, bf16_t>(feat, pad, plan, (bf16_t*)z, arg, s, st)
+            : ctb::bin_scatter<false, float>(feat, pad, plan, (float*)z, arg, s, st);
+}
+
+inline bool binned_ok(const ctb_shape* s) {
+  ctb::BinConfig bc;
+  return ctb::bin_config(s, false, &bc);      // the max variant needs the larger footprint
+}
+// TILE mode takes the binned scatters only where they win (measured, profiles/r02_*): the sums on every dense grid
+// (at least one point per four cells), the max on coarse grids (<= 1024 cells: the whole unit is one tile and every
+// window gets a long run of entries).  DETERMINISTIC always takes them.
+inline bool binned_in_tile(const ctb_shape* s, bool sum) {
+  static const bool off = getenv("CTB_NO_BINNED") != nullptr;
+  static const bool all = getenv("CTB_BINNED_ALL") != nullptr;
+  if (off || !binned_ok(s)) return false;
+  if (all) return true;
+  return ctb::plan_dense(s) && (sum || ctb::shape_cells(s) <= 1024);
+}
+
 #define CTB_DISPATCH_DIM(shape, call2, call3) ((shape)->dim == 2 ? (call2) : (call3))
 
 }  // namespace
@@ -304,27 +331,32 @@ int ctb_mode_supported(const ctb_shape* shape, int op, int reduce, int mode) {
   if (mode != CTB_MODE_TILE && mode != CTB_MODE_DETERMINISTIC) return 0;
   const bool sum = reduce == CTB_REDUCE_SUM;
   const bool det = mode == CTB_MODE_DETERMINISTIC;
-  ctb::ScatterConfig sc;
   ctb::TileConfig tc;
   ctb::TileConfig gc;
+  // DETERMINISTIC: the two scatters are the binned kernels (fixed summation order); TILE uses them too when the
+  // caller hands in a plan, and the shared-memory tile scatters otherwise
   switch (op) {
     case CTB_OP_SPLAT_FWD:
-      return det ? (ctb::plan_supported(shape) && ctb::scatter_config(shape, sum, &sc))
-                 : ctb::tile_scatter_config(shape, sum, !sum, &tc);
+      return det ? binned_ok(shape) : (binned_in_tile(shape, sum) || ctb::tile_scatter_config(shape, sum, !sum, &tc));
     case CTB_OP_SPLAT_BWD: return sum ? 0 : ctb::gather_config(shape, ctb::GATHER_SPLAT_BWD, &gc);
     case CTB_OP_SLICE_FWD: return ctb::gather_config(shape, ctb::GATHER_SLICE_FWD, &gc);
     case CTB_OP_SLICE_BWD:
-      return (det ? (ctb::plan_supported(shape) && ctb::scatter_config(shape, true, &sc))
-                  : ctb::tile_scatter_config(shape, true, false, &tc)) &&
+      return (det ? binned_ok(shape) : (binned_in_tile(shape, true) || ctb::tile_scatter_config(shape, true, false, &tc))) &&
              ctb::gather_config(shape, ctb::GATHER_SLICE_BWD_KEYS, &gc);
     default: return 0;
   }
 }
 
+int ctb_plan_used(const ctb_shape* shape, int mode) {
+  if (check_shape(shape, true)) return 0;
+  if (mode != CTB_MODE_TILE && mode != CTB_MODE_DETERMINISTIC) return 0;
+  return (mode == CTB_MODE_DETERMINISTIC ? binned_ok(shape) : binned_in_tile(shape, true)) ? 1 : 0;
+}
+
 size_t ctb_plan_bytes(const ctb_shape* shape) {
   if (check_shape(shape, false)) return 0;
   if (!ctb::plan_supported(shape)) return 0;
-  return ctb::sorted_plan_bytes(shape);
+  return ctb::plan_layout(shape).bytes;
 }
 
 int ctb_plan_build(const float* keys, void* plan, size_t plan_bytes, const ctb_shape* shape, void* stream) {
@@ -332,9 +364,9 @@ int ctb_plan_build(const float* keys, void* plan, size_t plan_bytes, const ctb_s
   if (st) return st;
   if (!keys || !plan) return CTB_ERR_INVALID_ARGUMENT;
   if (!ctb::plan_supported(shape)) return CTB_ERR_UNSUPPORTED;
-  if (plan_bytes < ctb::sorted_plan_bytes(shape)) return CTB_ERR_WORKSPACE;
-  return cuda_status(shape->dim == 2 ? ctb::sorted_plan_build<2>(keys, plan, shape, (cudaStream_t)stream)
-                                     : ctb::sorted_plan_build<3>(keys, plan, shape, (cudaStream_t)stream));
+  if (plan_bytes < ctb::plan_layout(shape).bytes) return CTB_ERR_WORKSPACE;
+  return cuda_status(shape->dim == 2 ? ctb::plan_build<2>(keys, plan, shape, (cudaStream_t)stream)
+                                     : ctb::plan_build<3>(keys, plan, shape, (cudaStream_t)stream));
 }
 
 int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pad, void* z_any, int32_t* arg,
@@ -345,13 +377,13 @@ int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pa
   if (!keys || !features || !z) return CTB_ERR_INVALID_ARGUMENT;
   if (reduce != CTB_REDUCE_MAX && reduce != CTB_REDUCE_SUM) return CTB_ERR_INVALID_ARGUMENT;
   if (reduce == CTB_REDUCE_MAX && !arg) return CTB_ERR_INVALID_ARGUMENT;
-  if (shape->grid_dtype != CTB_DTYPE_F32 && mode != CTB_MODE_TILE) return CTB_ERR_UNSUPPORTED;
-  if (mode == CTB_MODE_DETERMINISTIC) {
+  if (shape->grid_dtype != CTB_DTYPE_F32 && mode == CTB_MODE_ATOMIC) return CTB_ERR_UNSUPPORTED;
+  if (mode == CTB_MODE_DETERMINISTIC || (mode == CTB_MODE_TILE && plan && binned_in_tile(shape, reduce == CTB_REDUCE_SUM))) {
     if (!plan) return CTB_ERR_WORKSPACE;
+    if (!binned_ok(shape)) return CTB_ERR_UNSUPPORTED;
     const bool sum = reduce == CTB_REDUCE_SUM;
-    return cuda_status(shape->dim == 2
-                           ? ctb::sorted_scatter<2>(plan, features, pad, z, arg, shape, sum, (cudaStream_t)stream)
-                           : ctb::sorted_scatter<3>(plan, features, pad, z, arg, shape, sum, (cudaStream_t)stream));
+    return cuda_status(binned_dispatch(features, pad, plan, z_any, sum ? nullptr : arg, shape, sum,
+                                       (cudaStream_t)stream));
   }
   if (mode == CTB_MODE_TILE) {
     const bool sum = reduce == CTB_REDUCE_SUM;
@@ -414,12 +446,9 @@ int ctb_slice_bwd_keys(const float* keys, const void* grid_any, const float* pad
   if (mode == CTB_MODE_DETERMINISTIC || mode == CTB_MODE_TILE) {
     if (!ctb_mode_supported(shape, CTB_OP_SLICE_BWD, CTB_REDUCE_SUM, mode)) return CTB_ERR_UNSUPPORTED;
     // grad_grid: scatter-add of grad_out * pad (the Splat-sum kernel of the mode) ...
-    if (mode == CTB_MODE_DETERMINISTIC) {
+    if (mode == CTB_MODE_DETERMINISTIC || (plan && binned_in_tile(shape, true))) {
       if (!plan) return CTB_ERR_WORKSPACE;
-      if (shape->grid_dtype != CTB_DTYPE_F32) return CTB_ERR_UNSUPPORTED;
-      st = cuda_status(shape->dim == 2
-                           ? ctb::sorted_scatter<2>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream)
-                           : ctb::sorted_scatter<3>(plan, grad_out, pad, grad_grid, nullptr, shape, true, (cudaStream_t)stream));
+      st = cuda_status(binned_dispatch(grad_out, pad, plan, grad_grid_any, nullptr, shape, true, (cudaStream_t)stream));
     } else {
       st = cuda_status(scatter_dispatch(keys, grad_out, pad, grad_grid_any, nullptr, shape, true, (cudaStream_t)stream));
     }

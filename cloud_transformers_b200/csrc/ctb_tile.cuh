@@ -1218,6 +1218,11 @@ tile_gather_kernel(const float* __restrict__ keys, const GT* __restrict__ t1, co
     }
     }
   }
+  // launched with programmatic stream serialization behind the grad_grid scatter of Slice backward: nothing above
+  // reads what that kernel writes, but the grid must not RETIRE before it, or the next kernel on the stream could
+  // start while the scatter still runs (PTX: a dependent grid uses griddepcontrol.wait for correct ordering).
+  // Without the launch attribute this is a no-op.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 inline bool gather_config(const ctb_shape* s, int mode, TileConfig* out, bool aligned16 = true) {

@@ -21,11 +21,15 @@ _MODES = {"auto": None, "atomic": _lib.MODE_ATOMIC, "tile": _lib.MODE_TILE, "det
 class _Config:
     """Process-wide switches.  mode: 'auto' (shared-memory tile kernels when the shape is supported, else
     the point-stationary L2-atomic kernels), 'atomic', 'tile' or 'deterministic' (error if unsupported).
-    fused: let Splat / Slice bypass lc / idx when they were produced by our DifferentiablePositions."""
+    fused: let Splat / Slice bypass lc / idx when they were produced by our DifferentiablePositions.
+    use_plan: see below."""
 
     def __init__(self):
         self.mode = os.environ.get("CTB_MODE", "auto")
         self.fused = os.environ.get("CTB_FUSED", "1") != "0"
+        # tile mode: build the per-unit plan (sorted entry lists) where the plan-based scatters are faster; off = always
+        # the shared-memory tile scatters (fixed-point sums, invariant under permutations of the points)
+        self.use_plan = os.environ.get("CTB_USE_PLAN", "1") != "0"
 
 
 config = _Config()
@@ -223,6 +227,16 @@ class PositionsHandle:
                                 "shape not covered by the %s kernels" % want)
         return _lib.MODE_ATOMIC
 
+    def plan_for(self, mode, F):
+        """The plan if the kernels of `mode` use one on this shape (built once, shared by Splat fwd and Slice bwd)."""
+        if mode == _lib.MODE_ATOMIC or (mode == _lib.MODE_TILE and not config.use_plan):
+            return None
+        k = self.keys
+        sh = self.geom.shape(k.size(0), F, k.size(-1))
+        if not _lib.load().ctb_plan_used(ctypes.byref(sh), mode):
+            return None
+        return self.plan()
+
     def plan(self):
         if self._plan is None:
             k = self.keys_c()
@@ -240,8 +254,8 @@ class PositionsHandle:
 
 
 def _grid_dtype_code(dtype, mode):
-    """bf16 grids are handled natively by the TILE kernels; everything else goes through fp32."""
-    return _lib.DTYPE_BF16 if (dtype == torch.bfloat16 and mode == _lib.MODE_TILE) else _lib.DTYPE_F32
+    """bf16 grids are handled natively by the TILE / DETERMINISTIC kernels; everything else goes through fp32."""
+    return _lib.DTYPE_BF16 if (dtype == torch.bfloat16 and mode != _lib.MODE_ATOMIC) else _lib.DTYPE_F32
 
 
 def _grid_c(t, code):
@@ -257,7 +271,7 @@ class _FusedSplatFn(torch.autograd.Function):
         B, N = f_c.size(0), f_c.size(-1)
         F = f_c.size(1) // geom.heads
         mode = handle.mode_for(_lib.OP_SPLAT_FWD, F, reduce)
-        plan = handle.plan() if mode == _lib.MODE_DETERMINISTIC else None
+        plan = handle.plan_for(mode, F)
         gd = _grid_dtype_code(out_dtype, mode)
         ctx.gd = gd
         z = torch.empty((B, geom.heads * F) + geom.sizes,
@@ -321,8 +335,8 @@ class _FusedSliceFn(torch.autograd.Function):
         B, N = k.size(0), k.size(-1)
         F = g_c.size(1) // geom.heads
         mode = handle.mode_for(_lib.OP_SLICE_BWD, F)
-        plan = handle.plan() if mode == _lib.MODE_DETERMINISTIC else None
-        gd = _lib.DTYPE_BF16 if (g_c.dtype == torch.bfloat16 and mode == _lib.MODE_TILE) else _lib.DTYPE_F32
+        plan = handle.plan_for(mode, F)
+        gd = _grid_dtype_code(g_c.dtype, mode)
         if gd == _lib.DTYPE_F32 and g_c.dtype != torch.float32:
             g_c = g_c.float()
         go_c = _f32c(go)

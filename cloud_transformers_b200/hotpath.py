@@ -47,7 +47,8 @@ class HotPath:
         self.grad_keys_splat = torch.empty((B, H * dim, N), **f32)
         self.grad_feat = torch.empty((B, H * F, N), **f32)
         self.plan = None
-        if _lib.MODE_DETERMINISTIC in (self.modes[_lib.OP_SPLAT_FWD], self.modes[_lib.OP_SLICE_BWD]):
+        if any(m != _lib.MODE_ATOMIC and lib.ctb_plan_used(ctypes.byref(self.shape), m)
+               for m in (self.modes[_lib.OP_SPLAT_FWD], self.modes[_lib.OP_SLICE_BWD])):
             nbytes = lib.ctb_plan_bytes(ctypes.byref(self.shape))
             self.plan = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self._sh = ctypes.byref(self.shape)
@@ -69,6 +70,9 @@ class HotPath:
     def splat_fwd(self, keys, feat, pad=None):
         if self.plan is not None:
             self.build_plan(keys)
+        return self.splat_fwd_only(keys, feat, pad)
+
+    def splat_fwd_only(self, keys, feat, pad=None):
         _call("ctb_splat_fwd_keys", _ptr(keys), _ptr(feat), _ptr(pad), _ptr(self.z), _ptr(self.arg), self._sh,
               self.reduce, self.modes[_lib.OP_SPLAT_FWD], _ptr(self.plan), _stream(keys))
         return self.z

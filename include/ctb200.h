@@ -57,9 +57,10 @@ typedef enum ctb_reduce { CTB_REDUCE_MAX = 0, CTB_REDUCE_SUM = 1 } ctb_reduce;
  *                 grad_grid, Splat-sum) are accumulated as exact fixed-point integers (|err| <= 2^-24 |sum|
  *                 + N 2^-39 max|v|), so they are bit-identical from run to run and under any permutation of
  *                 the points; only inputs with Inf / NaN fall back to float atomics.  The fast path.
- *   DETERMINISTIC as TILE, but the two scatters walk entries sorted by destination cell (needs a plan,
- *                 see ctb_plan_build): every cell is reduced by one owner in ascending e = s*N + n with
- *                 plain stores -- no atomics anywhere, bit-identical from run to run. */
+ *   DETERMINISTIC as TILE, but the two scatters are REQUIRED to be the output-stationary kernels over the plan
+ *                 (see ctb_plan_build): every cell is reduced by one owner in ascending e = s*N + n with plain
+ *                 fp32 adds and stores -- no atomics anywhere, bit-identical from run to run and equal to a
+ *                 sequential loop over the entries.  TILE uses the same kernels whenever it is given a plan. */
 typedef enum ctb_mode { CTB_MODE_ATOMIC = 0, CTB_MODE_DETERMINISTIC = 1, CTB_MODE_TILE = 2 } ctb_mode;
 
 /* element type of the GRID tensors (z, convolved grid, grad_grid, grad_z) of the fused entries.  BF16 is the storage
@@ -126,9 +127,16 @@ typedef enum ctb_op {
 /* 1 if `op` can run in `mode` on this shape (reduce only matters for the Splat ops). */
 int ctb_mode_supported(const ctb_shape* shape, int op, int reduce, int mode);
 
+/* The plan: the points of every (b, h) unit sorted (stably) by their base cell, built once per set of keys and
+ * shared by the operators that see those keys (an MHCT block feeds the same positions to Splat and Slice,
+ * layers/multihead_ct.py:99-107).  With a plan the two scatters (ctb_splat_fwd_keys, grad_grid of
+ * ctb_slice_bwd_keys) run output-stationary: every grid cell reduces the points of its 2^dim neighbouring bins in
+ * registers, in ascending e = s*N + n -- no atomics, fixed summation order.
+ * ctb_plan_used: 1 if the kernels of `mode` use a plan on this shape (then the caller should build one and pass it;
+ * DETERMINISTIC requires it, TILE falls back to its shared-memory tile scatters when plan == NULL). */
+int ctb_plan_used(const ctb_shape* shape, int mode);
 /* bytes of the plan for this shape, 0 if the shape cannot be planned. */
 size_t ctb_plan_bytes(const ctb_shape* shape);
-/* sort the S*N (point, corner) entries of every (b, h) unit by destination cell. */
 int ctb_plan_build(const float* keys, void* plan, size_t plan_bytes, const ctb_shape* shape, void* stream);
 
 /* grid tensors (z, grad_z, grid, grad_grid) are void*: f32 or bf16 according to shape->grid_dtype */
