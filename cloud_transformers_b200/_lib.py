@@ -58,6 +58,7 @@ SIGNATURES = {
     "ctb_slice_fwd_keys": (_I, [_P, _P, _P, _P, _SH, _I, _P]),
     "ctb_slice_bwd_keys": (_I, [_P, _P, _P, _P, _P, _P, _SH, _I, _P, _P]),
     "ctb_project_fwd": (_I, [_P, _P, ctypes.c_float, _P, _P, _P, _P, _SH, _P]),
+    "ctb_project_fwd_stats": (_I, [_P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _SH, _P]),
     "ctb_project_bwd": (_I, [_P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _SH, _P]),
     "ctb_project_bwd_workspace_bytes": (ctypes.c_size_t, [_SH]),
     "ctb_count_occupied": (_I, [_P, ctypes.c_uint64, _P, _P]),

@@ -467,21 +467,26 @@ int ctb_slice_bwd_keys(const float* keys, const void* grid_any, const float* pad
       (slice_bwd_atomic_impl<3, true>(src, grid, pad, grad_out, grad_grid, grad_keys, shape, stream)));
 }
 
-int ctb_project_fwd(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
-                    const float* scales, float* keys, const ctb_shape* shape, void* stream) {
+int ctb_project_fwd_stats(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
+                          const float* scales, float* keys, double* key_stats, const ctb_shape* shape, void* stream) {
   int st = check_shape(shape, false);
   if (st) return st;
   if (!pcd || !shift || !rot || !keys) return CTB_ERR_INVALID_ARGUMENT;
   const int chunks = (shape->N + ctb::kProjBlock - 1) / ctb::kProjBlock;
   const unsigned blocks = (unsigned)((long long)shape->B * shape->H * chunks);
   if (shape->dim == 2)
-    ctb::project_fwd_kernel<2><<<blocks, ctb::kProjBlock, 0, (cudaStream_t)stream>>>(pcd, keys_res, res_scale, shift, rot,
-                                                                                     scales, keys, shape->H, shape->N, chunks);
+    ctb::project_fwd_kernel<2><<<blocks, ctb::kProjBlock, 0, (cudaStream_t)stream>>>(
+        pcd, keys_res, res_scale, shift, rot, scales, keys, key_stats, shape->H, shape->N, chunks);
   else
-    ctb::project_fwd_kernel<3><<<blocks, ctb::kProjBlock, 0, (cudaStream_t)stream>>>(pcd, keys_res, res_scale, shift, rot,
-                                                                                     scales, keys, shape->H, shape->N, chunks);
+    ctb::project_fwd_kernel<3><<<blocks, ctb::kProjBlock, 0, (cudaStream_t)stream>>>(
+        pcd, keys_res, res_scale, shift, rot, scales, keys, key_stats, shape->H, shape->N, chunks);
   CTB_LAUNCH_CHECK();
   return CTB_OK;
+}
+
+int ctb_project_fwd(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
+                    const float* scales, float* keys, const ctb_shape* shape, void* stream) {
+  return ctb_project_fwd_stats(pcd, keys_res, res_scale, shift, rot, scales, keys, nullptr, shape, stream);
 }
 
 int ctb_project_bwd(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,

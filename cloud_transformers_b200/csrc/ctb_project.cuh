@@ -17,29 +17,48 @@ namespace ctb {
 constexpr int kProjBlock = 256;
 constexpr int kProjAcc = 16;   // per-head accumulator row: shift[3] R[9] scales[3] res_scale[1]
 
+// key_stats (optional, f64 [2], accumulated): sum and sum of squares of the pre-tanh keys q -- what the reference
+// logs per block as mean(keys) / var(keys) (layers/multihead_ct.py:109-113) -- so that the pre-tanh tensor never has to
+// be materialised for the statistics.
 template <int D>
 __global__ void __launch_bounds__(kProjBlock)
 project_fwd_kernel(const float* __restrict__ pcd, const float* __restrict__ res, float res_scale,
                    const float* __restrict__ shift, const float* __restrict__ rot, const float* __restrict__ scales,
-                   float* __restrict__ keys, int H, int N, int chunks) {
+                   float* __restrict__ keys, double* __restrict__ key_stats, int H, int N, int chunks) {
   const int unit = blockIdx.x / chunks;
   const int n = (blockIdx.x % chunks) * kProjBlock + threadIdx.x;
-  if (n >= N) return;
+  const bool live = n < N;
   const int b = unit / H, h = unit % H;
-  float p[3];
+  float s1 = 0.0f, s2 = 0.0f;
+  if (live) {
+    float p[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    p[c] = __ldg(pcd + ((size_t)b * 3 + c) * N + n);
-    if (res) p[c] += res_scale * __ldg(res + ((size_t)unit * 3 + c) * N + n);
-    p[c] += __ldg(shift + h * 3 + c);
+    for (int c = 0; c < 3; ++c) {
+      p[c] = __ldg(pcd + ((size_t)b * 3 + c) * N + n);
+      if (res) p[c] += res_scale * __ldg(res + ((size_t)unit * 3 + c) * N + n);
+      p[c] += __ldg(shift + h * 3 + c);
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float q = p[0] * __ldg(rot + h * 9 + j);
+      q = fmaf(p[1], __ldg(rot + h * 9 + 3 + j), q);
+      q = fmaf(p[2], __ldg(rot + h * 9 + 6 + j), q);
+      if (scales) q *= __ldg(scales + h * D + j);
+      keys[((size_t)unit * D + j) * N + n] = tanhf(q);
+      s1 += q;
+      s2 = fmaf(q, q, s2);
+    }
   }
-#pragma unroll
-  for (int j = 0; j < D; ++j) {
-    float q = p[0] * __ldg(rot + h * 9 + j);
-    q = fmaf(p[1], __ldg(rot + h * 9 + 3 + j), q);
-    q = fmaf(p[2], __ldg(rot + h * 9 + 6 + j), q);
-    if (scales) q *= __ldg(scales + h * D + j);
-    keys[((size_t)unit * D + j) * N + n] = tanhf(q);
+  if (key_stats != nullptr) {
+    double d1 = (double)s1, d2 = (double)s2;
+    for (int o = 16; o > 0; o >>= 1) {
+      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(key_stats, d1);
+      atomicAdd(key_stats + 1, d2);
+    }
   }
 }
 

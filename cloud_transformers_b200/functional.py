@@ -371,7 +371,7 @@ def count_occupied(z):
 # A8: fused per-head projection + tanh (VolTransformer / PlaneTransformer + torch.tanh of the MHCT blocks)
 class _ProjectFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pcd, keys_res, res_scale, shift, rot, scales, heads, dim):
+    def forward(ctx, pcd, keys_res, res_scale, shift, rot, scales, heads, dim, key_stats):
         _require_cuda(pcd, keys_res, shift, rot, scales)
         pcd_c, res_c = _f32c(pcd), _f32c(keys_res)
         shift_c, rot_c, scales_c = _f32c(shift), _f32c(rot), _f32c(scales)
@@ -380,8 +380,8 @@ class _ProjectFn(torch.autograd.Function):
         keys = torch.empty((B, heads * dim, N), dtype=torch.float32, device=pcd_c.device)
         sh = _lib.make_shape(B, heads, 1, N, dim, (2,) * dim)
         with torch.cuda.device(pcd_c.device):
-            _call("ctb_project_fwd", _ptr(pcd_c), _ptr(res_c), ctypes.c_float(rs), _ptr(shift_c), _ptr(rot_c),
-                  _ptr(scales_c), _ptr(keys), ctypes.byref(sh), _stream(pcd_c))
+            _call("ctb_project_fwd_stats", _ptr(pcd_c), _ptr(res_c), ctypes.c_float(rs), _ptr(shift_c), _ptr(rot_c),
+                  _ptr(scales_c), _ptr(keys), _ptr(key_stats), ctypes.byref(sh), _stream(pcd_c))
         ctx.save_for_backward(pcd_c, res_c, shift_c, rot_c, scales_c, keys)
         ctx.rs, ctx.heads, ctx.dim = rs, heads, dim
         ctx.res_scale_is_tensor = isinstance(res_scale, torch.Tensor)
@@ -408,12 +408,20 @@ class _ProjectFn(torch.autograd.Function):
         g_rot = acc[:, 3:12].reshape(heads, 3, 3)
         g_scales = acc[:, 12:12 + dim].contiguous() if scales_c is not None else None
         g_rs = acc[:, 15].sum() if ctx.res_scale_is_tensor else None
-        return g_pcd, g_res, g_rs, g_shift, g_rot, g_scales, None, None
+        return g_pcd, g_res, g_rs, g_shift, g_rot, g_scales, None, None, None
 
 
-def project_keys(orig_pcd, keys_res, shift, rot, scales=None, res_scale=None, *, heads, dim):
+def project_keys(orig_pcd, keys_res, shift, rot, scales=None, res_scale=None, *, heads, dim, key_stats=None):
     """tanh(((orig_pcd + res_scale * keys_res + shift) . rot)[:dim] * scales) -> keys [B, heads*dim, N].
 
     orig_pcd [B,3,N]; keys_res [B, heads*3, N] or [B,heads,3,N] or None; shift [heads,3]; rot [heads,3,3];
-    scales [heads,dim] or None; res_scale None / python float / 0-dim tensor (MultiHeadAdaIn's `scale`)."""
-    return _ProjectFn.apply(orig_pcd, keys_res, res_scale, shift, rot, scales, heads, dim)
+    scales [heads,dim] or None; res_scale None / python float / 0-dim tensor (MultiHeadAdaIn's `scale`).
+    key_stats: optional zeroed float64 [2] device tensor that receives sum / sum of squares of the PRE-tanh keys."""
+    return _ProjectFn.apply(orig_pcd, keys_res, res_scale, shift, rot, scales, heads, dim, key_stats)
+
+
+def key_mean_var(key_stats, count):
+    """mean and (unbiased, like torch.var) variance of the pre-tanh keys from the sums ctb_project_fwd_stats filled."""
+    mean = key_stats[0] / count
+    var = (key_stats[1] - key_stats[0] * mean) / max(count - 1, 1)
+    return mean.float(), var.float()

@@ -159,6 +159,11 @@ int ctb_slice_bwd_keys(const float* keys, const void* grid, const float* pad, co
  *   row-vector convention q_j = sum_c p_c rot[h][c][j]), scales f32 [H,dim] or NULL, keys f32 [B,H*dim,N]. */
 int ctb_project_fwd(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
                     const float* scales, float* keys, const ctb_shape* shape, void* stream);
+/* Same, and additionally accumulates into key_stats (f64 [2], device memory, caller zeroes; may be NULL) the sum and
+ * the sum of squares of the PRE-tanh keys: the mean / variance every MHCT block logs (layers/multihead_ct.py:109-113,
+ * multihead_ct_adain.py:127-131, multihead_ct_pool.py:76-80) without materialising the pre-tanh tensor. */
+int ctb_project_fwd_stats(const float* pcd, const float* keys_res, float res_scale, const float* shift, const float* rot,
+                          const float* scales, float* keys, double* key_stats, const ctb_shape* shape, void* stream);
 /* Backward of ctb_project_fwd.  grad_pcd f32 [B,3,N] (summed over heads), grad_keys_res f32 [B,H,3,N] or NULL,
  * param_acc f32 [H,16] ACCUMULATED into (caller zeroes): cols 0-2 d shift, 3-11 d rot (row major c,j; only j < dim
  * are written), 12-14 d scales, 15 d res_scale (per head; sum over heads for the scalar). */

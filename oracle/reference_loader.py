@@ -25,7 +25,21 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("CTB_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(_HERE, "_ref")          # verbatim copy made by oracle/stage_ref.py (travels to the GPU box)
+REPO_ROOT = os.path.dirname(_HERE)
+DROPIN_ROOT = os.path.join(REPO_ROOT, "dropin")
+
+
+def _pick_root():
+    env = os.environ.get("CTB_REFERENCE_ROOT")
+    for cand in (env, "/root/reference", STAGED_ROOT):
+        if cand and os.path.isfile(os.path.join(cand, "layers", "cloud_transform.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 class _ScatterMaxFirst(torch.autograd.Function):
@@ -114,3 +128,46 @@ def load_reference_layers():
         sys.path.remove(REFERENCE_ROOT)
     assert os.path.realpath(ct.__file__).startswith(os.path.realpath(REFERENCE_ROOT))
     return ct, ut, mh
+
+
+def _purge(prefixes=("layers", "unet2d", "utils", "model_zoo")):
+    for k in [k for k in sys.modules if any(k == p or k.startswith(p + ".") for p in prefixes)]:
+        del sys.modules[k]
+
+
+class reference_tree:
+    """Context manager: the reference's package tree (`layers`, `unet2d`, `utils`, ...) importable, with the two
+    dependency shims installed.  dropin=True puts this repo's `dropin/` FIRST on sys.path: the reference's `layers` is
+    a namespace package (no __init__.py), so `layers.cloud_transform` then resolves to dropin/layers/cloud_transform.py
+    (the B200 kernels) while every other module -- layers.multihead_ct*, layers.utils, unet2d.*, the model files --
+    is the reference's own, unmodified file.  That is exactly what a user does to switch."""
+
+    def __init__(self, dropin=False, root=None):
+        self.dropin = dropin
+        self.root = root or REFERENCE_ROOT
+
+    def __enter__(self):
+        if not os.path.isfile(os.path.join(self.root, "layers", "cloud_transform.py")):
+            raise RuntimeError("reference tree not present at %s (run oracle/stage_ref.py in the build container)" % self.root)
+        install_shims()
+        _purge()
+        self.added = ([DROPIN_ROOT] if self.dropin else []) + [self.root]
+        if self.dropin and REPO_ROOT not in sys.path:
+            sys.path.insert(0, REPO_ROOT)
+        for p in reversed(self.added):
+            sys.path.insert(0, p)
+        return self
+
+    def __exit__(self, *exc):
+        for p in self.added:
+            if p in sys.path:
+                sys.path.remove(p)
+        _purge()
+        return False
+
+    def load_model(self, rel_path, **params):
+        """exec the model file like utils/train_util.py:23-27 get_model() and instantiate its `Model`."""
+        env = {}
+        with open(os.path.join(self.root, rel_path), "r") as f:
+            exec(compile(f.read(), os.path.join(self.root, rel_path), "exec"), env)
+        return env["Model"](**params)

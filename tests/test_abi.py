@@ -127,3 +127,25 @@ def test_mhct_mirror_state_dict_matches_reference():
     ref = mh.MultiHeadUnion(model_dim=32, features_dims=[4, 4], tensor_sizes=[16, 8], tensor_dims=[2, 3], heads=[4, 4])
     ours = mhct.MultiHeadUnion(model_dim=32, features_dims=[4, 4], tensor_sizes=[16, 8], tensor_dims=[2, 3], heads=[4, 4])
     ours.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_dropin_resolves_inside_the_reference_tree():
+    """X4 plumbing (no GPU): with dropin/ ahead of the reference tree, `layers.cloud_transform` is ours and every other
+    module is the reference's; the classifier builds with the reference's parameter / buffer names."""
+    from oracle import reference_loader as RL
+    if not RL.available():
+        pytest.skip("no reference tree (neither /root/reference nor oracle/_ref)")
+    import torch
+    with RL.reference_tree(dropin=False) as rt:
+        torch.manual_seed(0)
+        ref_keys = {k: tuple(v.shape) for k, v in rt.load_model("model_zoo/scanobject/classifier.py").state_dict().items()}
+    with RL.reference_tree(dropin=True) as rt:
+        torch.manual_seed(0)
+        model = rt.load_model("model_zoo/scanobject/classifier.py")
+        import layers.cloud_transform as ct
+        import layers.multihead_ct as mh
+        assert os.path.realpath(ct.__file__).startswith(os.path.realpath(RL.DROPIN_ROOT))
+        assert os.path.realpath(mh.__file__).startswith(os.path.realpath(rt.root))
+        ours = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert ours == ref_keys
+    assert sum(1 for k in ours if k.endswith("tensor_mod")) == 76
