@@ -13,7 +13,10 @@ gradients) for all 24.  The grid convolution between Splat and Slice is outside 
   e2e    = same metric through the public modules (DifferentiablePositions / Splat / Slice + autograd) with
            HOST pinned inputs copied H2D every step and the loss read back D2H
   roofline = the op with the largest share of the step, algorithmic bytes / CUDA-event time
-  cpu_baseline = the reference's torch composition (oracle/ct_torch.py, kind "port") on the host cores
+  cpu_baseline = the reference's OWN layers/cloud_transform.py (staged verbatim in oracle/_ref by oracle/stage_ref.py,
+           imported under the two dependency shims; kind "reference") on the host cores
+  train  = MHCT training samples/s: the reference's own model_zoo/scanobject/classifier.py (24.02 M parameters)
+           running on the B200 kernels through dropin/, loop as train_classification.py:181-273
 Multi-GPU: weak scaling, every rank runs its own batch, no data-path collective.
 """
 import argparse
@@ -35,6 +38,56 @@ REPEATS = 4
 H, N_PTS, B_PER_GPU = 16, 2048, 32
 METRIC = "splat_slice_fwd_bwd_gpt_heads_per_s"
 UNIT = "Gpt-heads/s"
+# further BASELINE.json configs, timed as extra keys of the line: (name, dim, W, F, N, B, H)
+OTHER_CONFIGS = [("s3dis_a3d", 3, 32, 4, 4096, 8, 16), ("s3dis_b3d", 3, 16, 16, 4096, 8, 16),
+                 ("inpaint_dec_a2d", 2, 128, 4, 16384, 2, 16), ("inpaint_dec_a3d", 3, 32, 4, 16384, 2, 16),
+                 ("sweep_n256k_2d256", 2, 256, 4, 262144, 4, 16), ("sweep_h64_3d64", 3, 64, 4, 4096, 8, 64)]
+
+
+def workload_config(mode):
+    """the `config` object of the line: identical for both arms (the reference arm times a bounded sample of it)"""
+    step_bytes = 0
+    from_bytes = lambda N, d, F, C: N * (24 * d + 20 * F) + 24 * F * C      # SURVEY.md 8(d), fp32
+    for _, dim, W, F in CLASSES:
+        step_bytes += REPEATS * B_PER_GPU * H * from_bytes(N_PTS, dim, F, W ** dim)
+    return {"workload": "scanobjectnn_hotpath", "blocks_per_step": REPEATS * len(CLASSES), "batch_per_gpu": B_PER_GPU,
+            "heads": H, "points": N_PTS, "classes": [c[0] for c in CLASSES],
+            "l2": "working set per step %.1f GB >> 126 MB L2; same class never back to back" % (step_bytes / 1e9)}
+
+
+def reference_tree_root():
+    """where the unmodified reference files are: $CTB_REFERENCE_ROOT, the build container's /root/reference, or the
+    verbatim copy staged by oracle/stage_ref.py (the only one that exists on the GPU box)"""
+    for cand in (os.environ.get("CTB_REFERENCE_ROOT"), "/root/reference", os.path.join(ROOT, "oracle", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "layers", "cloud_transform.py")):
+            return cand
+    return None
+
+
+def load_reference_model_through_dropin(rel_path, **params):
+    """What a user of the reference does to switch: dropin/ ahead of the reference checkout on
+    sys.path.  `layers` has no __init__.py (namespace package), so layers.cloud_transform resolves to
+    dropin/layers/cloud_transform.py and everything else -- layers.multihead_ct*, unet2d.*, the model file, exec'd as
+    in utils/train_util.py:23-27 -- is the reference's own, unmodified code."""
+    root = reference_tree_root()
+    if root is None:
+        raise RuntimeError("no reference tree (run oracle/stage_ref.py in the build container)")
+    for k in [k for k in sys.modules if k.split(".")[0] in ("layers", "unet2d", "utils", "model_zoo")]:
+        del sys.modules[k]
+    paths = [os.path.join(ROOT, "dropin"), root]
+    try:
+        import pytorch3d.transforms.so3  # noqa: F401
+    except Exception:
+        paths.insert(0, os.path.join(ROOT, "dropin", "_optional_shims"))
+    for pth in reversed(paths):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    env = {}
+    with open(os.path.join(root, rel_path)) as f:
+        exec(compile(f.read(), os.path.join(root, rel_path), "exec"), env)
+    import layers.cloud_transform as ct
+    assert os.path.realpath(ct.__file__).startswith(os.path.realpath(os.path.join(ROOT, "dropin")))
+    return env["Model"](**params), root
 
 
 def peak_hbm():
@@ -148,6 +201,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")     # (CUDA-graph capture of NCCL collectives)
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     ctb.config.mode = args.mode
@@ -187,14 +241,11 @@ def run_ours(args):
         step()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        tms = torch.tensor([ms], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    from cloud_transformers_b200.sharding import aggregate_throughput
+    units, ms = aggregate_throughput(pt_heads_step, e0.elapsed_time(e1), dev)      # sum of units, max of time over ranks
     barrier()
     ms_per_step = ms / args.steps
-    value = world * pt_heads_step / (ms_per_step * 1e-3) / 1e9
+    value = units / (ms_per_step * 1e-3) / 1e9
 
     # ---- per-op CUDA-event timing for the roofline (same stream, same buffers, after the timed region)
     ops = []
@@ -203,6 +254,7 @@ def run_ours(args):
         keys, feat, conv, go, gz = data[name]
         hp = paths[name]
         ab = algorithmic_bytes(N_PTS, dim, F, W ** dim, e_grid=eg)
+        # (splat_fwd includes the plan build where the class uses one: it is part of the path)
         calls = {"splat_fwd": lambda: hp.splat_fwd(keys, feat), "slice_fwd": lambda: hp.slice_fwd(keys, conv),
                  "slice_bwd": lambda: hp.slice_bwd(keys, conv, go), "splat_bwd": lambda: hp.splat_bwd(keys, feat, gz)}
         for op, fn in calls.items():
@@ -226,7 +278,7 @@ def run_ours(args):
 
     # ---- context: the same step with the grids stored as bf16 (fp32 arithmetic; tolerance rel 1e-2, not the headline)
     bf16_mode = None
-    if args.grid_dtype == "f32" and rank == 0:
+    if args.grid_dtype == "f32" and rank == 0 and "bf16" not in args.skip.split(","):
         try:
             g2 = torch.Generator(device=dev).manual_seed(43)
             d16, p16 = {}, {}
@@ -256,64 +308,102 @@ def run_ours(args):
             bf16_mode = {"unavailable": repr(exc)[:200]}
 
     # ---- e2e through the public modules with host buffers -----------------------------------------
-    e2e = run_e2e(args, dev, world, rank, data, order)
-    ref_gpu = reference_composition_on_gpu(dev, data) if rank == 0 else None
+    skip = set(args.skip.split(","))
+    e2e = run_e2e(args, dev, world, rank, data, order) if "e2e" not in skip else None
+    ref_gpu = reference_composition_on_gpu(dev, data) if (rank == 0 and "refgpu" not in skip) else None
+    det_mode = run_deterministic(args, dev, data, order) if (rank == 0 and args.mode == "auto" and "det" not in skip) else None
     n_launches = args.steps * sum(paths[n].launches_per_pass() for n, _, _, _ in order)
     del data, paths
     torch.cuda.empty_cache()
-    train = run_train(args, dev, world, rank) if args.train_steps > 0 else None
+    others = run_other_configs(args, dev) if (rank == 0 and "others" not in skip) else None
+    barrier()
+    train = train_eager = None
+    if args.train_steps > 0 and "train" not in skip:
+        train_eager = run_train(args, dev, world, rank, graphed=False)
+        torch.cuda.empty_cache()
+        barrier()
+        train = run_train(args, dev, world, rank, graphed=True)
+        if "unavailable" in train:          # capture failed: the eager loop is the number
+            train, train_eager = train_eager, train
 
     if rank == 0:
-        cpu = cpu_baseline(sample_batch=8, repeats=3)
+        cpu = cpu_baseline() if "cpu" not in skip else None
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.grid_dtype == "f32" else "f32 arithmetic, bf16 grid storage", "data": "synthetic",
-            "config": {"workload": "scanobjectnn_hotpath", "blocks_per_step": len(order), "batch_per_gpu": B,
-                       "heads": H, "points": N_PTS, "classes": [c[0] for c in CLASSES], "mode": args.mode,
-                       "l2": "working set per step %.1f GB >> 126 MB L2; same class never back to back" %
-                             (step_bytes / 1e9)},
+            "config": workload_config(args.mode),
+            "mode": args.mode,
             "algorithmic_gbs": round(step_bytes / (ms_per_step * 1e-3) / 1e9, 1),
             "frac_of_hbm_peak": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
-            "roofline": {"bound": "hbm", "kernel": "%s/%s" % (top["op"], top["class"]), "achieved": top["gbs"],
-                         "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": round(top["gbs"] / peak, 4),
-                         "traffic": ncu_traffic(top["op"], top["class"]), "algorithmic_bytes": top["bytes"],
+            "roofline": {"bound": "hbm", "op": "%s/%s" % (top["op"], top["class"]), "kernel": kernel_of(top["op"], top["class"]),
+                         "achieved": top["gbs"], "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                         "frac": round(top["gbs"] / peak, 4), "traffic": ncu_traffic(top["op"], top["class"]),
+                         "traffic_source": NCU_SUMMARY, "algorithmic_bytes": top["bytes"],
                          "share_of_step": round(top["ms"] / total_op_ms, 4)},
             "ops": ops,
             "e2e": e2e,
             "train": train,
+            "train_eager": train_eager,
             "gpu_launches": n_launches,
             "clocks": clocks,
             "cpu_baseline": cpu,
             "reference_composition_gpu": ref_gpu,
             "bf16_grid_mode": bf16_mode,
+            "deterministic_mode": det_mode,
+            "other_configs": others,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def ncu_traffic(op, cls):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel(s) of one op, per launch, from the committed
-    `ncu --set full` capture of tools/profile_ops.py (profiles/r01_ncu_full_summary.csv: 5 kernels per class in the order
-    Splat fwd | Slice fwd | Slice bwd scatter, Slice bwd gather | Splat bwd; classes in CLASSES order)."""
+NCU_SUMMARY = "profiles/r02_ncu_full_summary.csv"
+
+
+def _ncu_rows():
+    """rows of the committed `ncu --set full` summary (tools/ncu_summary.py over tools/profile_ops.py: per class the
+    kernels in launch order -- [plan] | Splat fwd | Slice fwd | Slice bwd scatter, Slice bwd gather | Splat bwd)."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.csv")
+    path = os.path.join(ROOT, NCU_SUMMARY)
+    rows = list(csv.reader(open(path)))
+    hdr, body = rows[0], rows[1:]
+    per_class, i = {}, 0
+    for name, _, _, _ in CLASSES:
+        ks = {}
+        if i < len(body) and body[i][0].startswith("plan_build"):
+            ks["plan"] = body[i]
+            i += 1
+        for key in ("splat_fwd", "slice_fwd", "slice_bwd_scatter", "slice_bwd_gather", "splat_bwd"):
+            ks[key] = body[i]
+            i += 1
+        per_class[name] = ks
+    return hdr, per_class
+
+
+def kernel_of(op, cls):
+    """name of the dominant kernel of an op (slice_bwd is two kernels: the grad_grid scatter dominates)"""
     try:
-        rows = list(csv.reader(open(path)))
-        hdr = rows[0]
+        _, pc = _ncu_rows()
+        key = {"slice_bwd": "slice_bwd_scatter"}.get(op, op)
+        return pc[cls][key][0]
+    except Exception:
+        return None
+
+
+def ncu_traffic(op, cls):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel(s) of one op, per launch, from the committed ncu
+    capture of the same library (profiles/r02_ncu_full_summary.csv); None if the file is missing or malformed."""
+    try:
+        hdr, pc = _ncu_rows()
         ir = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum")][0]
         iw = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum")][0]
-        unit_r, unit_w = hdr[ir], hdr[iw]
         scale = lambda u: 1e9 if "Gbyte" in u else (1e6 if "Mbyte" in u else (1e3 if "Kbyte" in u else 1.0))
-        ci = [c[0] for c in CLASSES].index(cls)
-        pick = {"splat_fwd": [0], "slice_fwd": [1], "slice_bwd": [2, 3], "splat_bwd": [4]}[op]
-        body = rows[1:]
-        if len(body) < 5 * len(CLASSES):
-            return None
-        return int(sum(float(body[ci * 5 + k][ir]) * scale(unit_r) + float(body[ci * 5 + k][iw]) * scale(unit_w)
-                       for k in pick))
+        keys = {"splat_fwd": ["plan", "splat_fwd"], "slice_fwd": ["slice_fwd"],
+                "slice_bwd": ["slice_bwd_scatter", "slice_bwd_gather"], "splat_bwd": ["splat_bwd"]}[op]
+        return int(sum(float(pc[cls][k][ir]) * scale(hdr[ir]) + float(pc[cls][k][iw]) * scale(hdr[iw])
+                       for k in keys if k in pc[cls]))
     except Exception:
         return None
 
@@ -331,8 +421,8 @@ def flush_l2(dev):
 def run_e2e(args, dev, world, rank, data, order):
     """Same step through DifferentiablePositions / Splat / Slice + autograd, inputs in pinned host memory."""
     import torch
-    import torch.distributed as dist
     import cloud_transformers_b200 as ctb
+    from cloud_transformers_b200.sharding import aggregate_throughput
     mods, host = {}, {}
     for name, dim, W, F in CLASSES:
         mods[name] = (ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim).to(dev),
@@ -344,29 +434,34 @@ def run_e2e(args, dev, world, rank, data, order):
     h2d = sum(host[n][0].numel() * 4 + host[n][1].numel() * 4 for n, _, _, _ in order)
     loss_host = torch.zeros(len(order), dtype=torch.float32).pin_memory()
 
-    # Input pipeline: the next block's host->device copies run on a copy stream while the current block computes
-    # (one block of prefetch).  Every copy still starts after the step's first timing event and is waited on by the
-    # compute stream, so the timed region covers all of them.
-    copy_stream = torch.cuda.Stream(device=dev)
+    # Input pipeline: the host->device copies of the next DEPTH blocks are in flight on two copy streams (keys on one,
+    # features on the other) while the current block computes.  Every copy still starts after the step's first timing
+    # event and is waited on by the compute stream, so the timed region covers all of them.
+    DEPTH = 3
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
 
     def upload(name):
-        with torch.cuda.stream(copy_stream):
-            k = host[name][0].to(dev, non_blocking=True)
-            f = host[name][1].to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return k, f, ev
+        out = []
+        for st, src in zip(streams, host[name]):
+            with torch.cuda.stream(st):
+                t = src.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            out.append((t, ev))
+        return out
 
     def step():
         main = torch.cuda.current_stream()
-        copy_stream.wait_stream(main)
-        nxt = upload(order[0][0])
+        for st in streams:
+            st.wait_stream(main)
+        queue = [upload(order[i][0]) for i in range(min(DEPTH, len(order)))]
         for i, (name, dim, W, F) in enumerate(order):
             dp, sp, sl = mods[name]
-            k, f, ev = nxt
-            if i + 1 < len(order):
-                nxt = upload(order[i + 1][0])
-            main.wait_event(ev)
+            (k, evk), (f, evf) = queue.pop(0)
+            if i + DEPTH < len(order):
+                queue.append(upload(order[i + DEPTH][0]))
+            main.wait_event(evk)
+            main.wait_event(evf)
             k.record_stream(main)
             f.record_stream(main)
             k.requires_grad_(True)
@@ -383,24 +478,96 @@ def run_e2e(args, dev, world, rank, data, order):
     steps = max(2, min(args.steps, 5))
     for _ in range(2):
         step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    _barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    units, ms = aggregate_throughput(len(order) * B_PER_GPU * H * N_PTS, e0.elapsed_time(e1) / steps, dev)
+    return {"value": round(units / (ms * 1e-3) / 1e9, 4), "unit": UNIT, "ms_per_step": round(ms, 3),
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(order),
+            "h2d_gbs_per_gpu": round(h2d / (ms * 1e-3) / 1e9, 1),
+            "api": "DifferentiablePositions/Splat/Slice modules + autograd",
+            "input_pipeline": "pinned host buffers, %d blocks of H2D prefetch on two copy streams; the step is bound by "
+                              "the host link when h2d_gbs_per_gpu is near the PCIe rate of the box" % DEPTH}
+
+
+def _barrier(world):
+    import torch
+    import torch.distributed as dist
     if world > 1:
-        tms = torch.tensor([ms], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    val = world * len(order) * B_PER_GPU * H * N_PTS / (ms * 1e-3) / 1e9
-    return {"value": round(val, 4), "unit": UNIT, "ms_per_step": round(ms, 3), "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": 4 * len(order), "api": "DifferentiablePositions/Splat/Slice modules + autograd",
-            "input_pipeline": "pinned host buffers, one block of H2D prefetch on a copy stream"}
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def run_other_configs(args, dev):
+    """The other BASELINE.json configs (S3DIS block, completion decoder, two sweep corners) and the deterministic
+    mode of the main workload: ms per fwd+bwd pass and Gpt-heads/s, C-ABI calls, inputs resident, this rank only."""
+    import torch
+    from cloud_transformers_b200.hotpath import HotPath, algorithmic_bytes
+    peak, _ = peak_hbm()
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(5)
+    for name, dim, W, F, N, B, heads in OTHER_CONFIGS:
+        try:
+            keys = torch.tanh(torch.randn(B, heads * dim, N, generator=gen, device=dev))
+            feat = torch.randn(B, heads * F, N, generator=gen, device=dev)
+            grid = (B, heads * F) + (W,) * dim
+            conv = torch.randn(grid, generator=gen, device=dev)
+            gz = torch.randn(grid, generator=gen, device=dev)
+            go = torch.randn(B, heads * F, N, generator=gen, device=dev)
+            hp = HotPath(W, heads, dim, B, F, N, dev, mode=args.mode)
+            for _ in range(2):
+                hp.fwd_bwd(keys, feat, conv, go, gz)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                flush_l2(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                hp.fwd_bwd(keys, feat, conv, go, gz)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            ms = statistics.median(ts)
+            nbytes = algorithmic_bytes(N, dim, F, W ** dim)["total"] * B * heads
+            modes = {0: "atomic", 1: "deterministic", 2: "tile"}
+            out[name] = {"shape": {"dim": dim, "W": W, "F": F, "N": N, "B": B, "H": heads}, "ms": round(ms, 4),
+                         "gpt_heads_per_s": round(B * heads * N / ms / 1e6, 4),
+                         "frac_of_hbm_peak": round(nbytes / ms / 1e6 / peak, 4),
+                         "kernels": [modes[m] for m in hp.modes]}
+            del hp, keys, feat, conv, gz, go
+        except Exception as exc:  # noqa: BLE001
+            out[name] = {"unavailable": repr(exc)[:160]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_deterministic(args, dev, data, order):
+    """The main workload with mode = deterministic (plan-based scatters with a fixed summation order)."""
+    import torch
+    from cloud_transformers_b200.hotpath import HotPath
+    try:
+        paths = {name: HotPath(W, H, dim, B_PER_GPU, F, N_PTS, dev, mode="deterministic") for name, dim, W, F in CLASSES}
+
+        def step():
+            for name, dim, W, F in order:
+                paths[name].fwd_bwd(*data[name])
+        step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        return {"value": round(len(order) * B_PER_GPU * H * N_PTS / (ms * 1e-3) / 1e9, 4), "unit": UNIT,
+                "ms_per_step": round(ms, 3), "what": "same step, mode = deterministic, this rank only"}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": repr(exc)[:200]}
 
 
 def reference_composition_on_gpu(dev, data):
@@ -432,120 +599,198 @@ def reference_composition_on_gpu(dev, data):
         torch.cuda.empty_cache()
 
 
-def run_train(args, dev, world, rank):
-    """Second half of the BASELINE metric: MHCT training samples/s.  A ScanObjectNN-classifier-shaped trunk built from
-    the block mirrors (cloud_transformers_b200/mhct.py: 12 MultiHeadUnion + 2 MultiHeadPool, 24 Splat + 24 Slice + 2
-    pool Splats per forward, like model_zoo/scanobject/classifier.py), Adam, cross-entropy on synthetic labels, clouds
-    copied from pinned host memory every step; DDP + SyncBatchNorm over NCCL when world > 1 (what
-    train_classification.py:107-109 does).  Convolutions / BatchNorm / Linear are stock PyTorch."""
+def run_train(args, dev, world, rank, graphed):
+    """Second half of the BASELINE metric: MHCT training samples/s on the reference's OWN ScanObjectNN classifier
+    (model_zoo/scanobject/classifier.py, 24.02 M parameters) running on the B200 kernels through dropin/.  The loop is
+    train_classification.py:181-273 on synthetic clouds (configs/scanobjectnn.yaml: Adam 1e-3, StepLR, seg_weight 0.5):
+    DDP(SyncBatchNorm.convert_sync_batchnorm(model)) as :107-109, loss = 0.5 CE + 0.5 BCE, optimizer step, then the
+    script's per-step bookkeeping -- utils/train_util_distributed.py reduce_loss_dict (:12-34) and the pickled
+    all_gather of predictions (:37-77), the reference's own unmodified functions -- and the .item() reads of the losses
+    and of the 26 x 3 lattice statistics rank 0 logs (:249-260).  Clouds come from pinned host memory every step.
+    graphed=True: forward + backward + optimizer step (SyncBN / DDP collectives included) replay as ONE CUDA graph
+    (cloud_transformers_b200/graphed.py); the bookkeeping stays eager, after the replay."""
     import torch
     import torch.distributed as dist
-    from cloud_transformers_b200.mhct import ScanObjectTrunk
+    from cloud_transformers_b200.graphed import GraphedTrainStep
+    from cloud_transformers_b200.sharding import aggregate_throughput
     try:
-        torch.manual_seed(1234 + rank)
-        torch.backends.cudnn.benchmark = True          # as train_classification.py:58
+        torch.manual_seed(42)                          # train_classification.py:96
+        torch.backends.cudnn.benchmark = True          # :58
         B = args.train_batch
-        model = ScanObjectTrunk().to(dev)
+        model, root = load_reference_model_through_dropin("model_zoo/scanobject/classifier.py")
+        import utils.train_util_distributed as tud     # the reference's own helpers
+        n_params = sum(p.numel() for p in model.parameters())
+        model = model.to(dev)
+        side = torch.cuda.Stream(device=dev)
         if world > 1:
-            model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-            # SyncBN keeps the running statistics identical on all ranks, so the per-step buffer broadcast of stock
-            # DDP is redundant; gradients are reduced in place in the buckets
-            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=False,
-                                                              gradient_as_bucket_view=True)
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):              # (the graph recipe wants DDP built on the warm-up stream)
+                model = torch.nn.parallel.DistributedDataParallel(torch.nn.SyncBatchNorm.convert_sync_batchnorm(model),
+                                                                  device_ids=[dev.index], output_device=dev.index)
+            torch.cuda.current_stream().wait_stream(side)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0, capturable=graphed)
+        sched = torch.optim.lr_scheduler.StepLR(opt, gamma=0.7, step_size=25000)
+        ce, bce = torch.nn.CrossEntropyLoss(), torch.nn.BCEWithLogitsLoss()
         gen = torch.Generator(device=dev).manual_seed(7 + rank)
-        clouds = [surface_clouds(gen, B, N_PTS, dev).cpu().pin_memory() for _ in range(4)]
+        clouds = [surface_clouds(gen, B, N_PTS, dev).permute(0, 2, 1).contiguous().cpu().pin_memory() for _ in range(4)]
         labels = [torch.randint(0, 15, (B,)).pin_memory() for _ in range(4)]
-        loss_host = torch.zeros(1).pin_memory()
+        masks = [(torch.rand(B, N_PTS) < 0.7).float().pin_memory() for _ in range(4)]
+        sink = []
+        model.train()
+
+        def loss_fn(outs, mask, y):
+            class_pred, mask_pred, lattices = outs
+            seg_loss = bce(mask_pred[:, 0, 0], mask)
+            cls_loss = ce(class_pred, y)
+            return 0.5 * cls_loss + 0.5 * seg_loss, (cls_loss, seg_loss)
+
+        def batch(i):
+            pcd = clouds[i % 4].to(dev, non_blocking=True).permute(0, 2, 1)[:, :, None]     # [B,3,1,N], :195
+            return pcd, masks[i % 4].to(dev, non_blocking=True), labels[i % 4].to(dev, non_blocking=True)
+
+        runner = None
+        if graphed:
+            pcd, mask, y = batch(0)
+            runner = GraphedTrainStep(model, opt, loss_fn, (pcd.contiguous(), mask, y))
 
         def step(i):
-            pcd = clouds[i % 4].to(dev, non_blocking=True)
-            y = labels[i % 4].to(dev, non_blocking=True)
-            logits, _ = model(pcd)
-            loss = torch.nn.functional.cross_entropy(logits, y)
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            opt.step()
-            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            pcd, mask, y = batch(i)
+            if runner is not None:
+                (class_pred, mask_pred, lattices), loss, (cls_loss, seg_loss) = runner(pcd, mask, y)
+            else:
+                outs = model(pcd)
+                class_pred, mask_pred, lattices = outs
+                loss, (cls_loss, seg_loss) = loss_fn(outs, mask, y)
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+            if world > 1:                                                                     # gather_results, :157-174
+                loss_all = tud.reduce_loss_dict({"loss": loss.detach(), "loss_cls": cls_loss.detach(),
+                                                 "loss_seg": seg_loss.detach()})
+            else:
+                loss_all = {"loss": loss, "loss_cls": cls_loss, "loss_seg": seg_loss}
+            with torch.no_grad():
+                pred_np = class_pred.detach().cpu().numpy().argmax(1)
+                mpred_np = (torch.sigmoid(mask_pred[:, 0, 0]) > 0.5).detach().cpu().numpy()
+                mask_np, y_np = mask.detach().cpu().numpy(), y.detach().cpu().numpy()
+            gathered = tud.all_gather((pred_np, mpred_np, y_np, mask_np)) if world > 1 else [(pred_np, mpred_np, y_np, mask_np)]
+            if rank == 0:                                                                     # tensorboard scalars, :249-260
+                sink.append([loss_all[k].item() for k in loss_all] +
+                            [float(v[0]) + v[1].item() + v[2].item() for v in lattices] + [len(gathered)])
+            sched.step()
 
-        for i in range(5 if world > 1 else 3):      # (DDP rebuilds its buckets after the first step)
+        for i in range(6 if world > 1 else 4):      # (DDP rebuilds its buckets after the first step; cudnn.benchmark)
             step(i)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        _barrier(world)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.train_steps):
             step(i)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.train_steps
-        if world > 1:
-            tms = torch.tensor([ms], device=dev)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms = float(tms.item())
-        n_params = sum(p.numel() for p in model.parameters())
-        return {"samples_per_s": round(world * B / (ms * 1e-3), 2), "ms_per_step": round(ms, 2), "batch_per_gpu": B,
+        units, ms = aggregate_throughput(B, e0.elapsed_time(e1) / args.train_steps, dev)
+        return {"samples_per_s": round(units / (ms * 1e-3), 2), "ms_per_step": round(ms, 2), "batch_per_gpu": B,
                 "points": N_PTS, "steps": args.train_steps, "params_m": round(n_params / 1e6, 2),
-                "final_loss": round(float(loss_host[0]), 4),
-                "model": "ScanObjectTrunk (classifier.py trunk: 12 MultiHeadUnion + 2 MultiHeadPool; towers -> avgpool)",
+                "final_loss": round(sink[-1][0], 4) if sink else None,
+                "model": "model_zoo/scanobject/classifier.py (reference file, unmodified) through dropin/",
+                "loop": "train_classification.py:181-273: DDP + SyncBN (:107-109), Adam + StepLR, reduce_loss_dict + pickled "
+                        "all_gather + .item() logging every step",
+                "step_execution": "one CUDA graph per step (forward + backward + optimizer + SyncBN / DDP collectives), "
+                                  "bookkeeping eager" if graphed else "eager, as the script",
                 "parallelism": "dp%d (DDP + SyncBN over NCCL)" % world if world > 1 else "single GPU"}
     except Exception as exc:
-        return {"unavailable": repr(exc)[:300]}
+        import traceback
+        return {"unavailable": repr(exc)[:300], "trace": traceback.format_exc()[-900:]}
 
 
-def cpu_step(sample_batch, threads):
-    """One bounded sample of the workload on the host: the six shape classes once each at batch
-    `sample_batch` through the reference's torch composition (oracle/ct_torch.py)."""
+# ---- the reference's own CPU implementation of the path (cpu_baseline leg and --impl reference) ------------------
+_REF_MODS = {}
+
+
+def _reference_modules():
+    """layers/cloud_transform.py of the reference, unmodified, imported from the staged tree under the two dependency
+    shims (torch_scatter.scatter_max, pytorch3d so3) of oracle/reference_loader.py."""
+    if not _REF_MODS:
+        from oracle import reference_loader as RL
+        if RL.available():
+            ct, _, _ = RL.load_reference_layers()
+            _REF_MODS["ct"] = ct
+            _REF_MODS["kind"] = "reference"
+        else:
+            from oracle import ct_torch as T
+            _REF_MODS["port"] = T
+            _REF_MODS["kind"] = "port"
+    return _REF_MODS
+
+
+def cpu_step(sample_batch, threads, repeats_per_class=1):
+    """One bounded sample of the workload on the host: the six shape classes at batch `sample_batch` through the
+    reference's own DifferentiablePositions / Splat / Slice modules, forward and backward."""
     import torch
-    from oracle import ct_torch as T
+    mods = _reference_modules()
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(0)
     t0 = time.perf_counter()
     for name, dim, W, F in CLASSES:
         keys = torch.tanh(torch.randn(sample_batch, H * dim, N_PTS, generator=g))
         feat = torch.randn(sample_batch, H * F, N_PTS, generator=g)
-        T.hot_path_fwd_bwd(keys, feat, W, H, dim)
+        for _ in range(repeats_per_class):
+            if "ct" in mods:
+                ct = mods["ct"]
+                k, f = keys.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+                lc, idx = ct.DifferentiablePositions(tensor_size=W, heads=H, dim=dim)(k)
+                z = ct.Splat(tensor_size=W, heads=H, dim=dim)(lc, idx, f)
+                out = ct.Slice(tensor_size=W, heads=H, dim=dim)(lc, idx, z)
+                out.square().mean().backward()
+            else:
+                mods["port"].hot_path_fwd_bwd(keys, feat, W, H, dim)
     dt = time.perf_counter() - t0
-    return len(CLASSES) * sample_batch * H * N_PTS / dt / 1e9, dt
+    return len(CLASSES) * repeats_per_class * sample_batch * H * N_PTS / dt / 1e9, dt
 
 
-def cpu_baseline(sample_batch=1, repeats=1):
-    import torch
+CPU_SAMPLE_BATCH = 8      # clouds per class in one CPU sample (the config's batch is 32; the metric is per point-head)
+
+
+def cpu_baseline(sample_batch=CPU_SAMPLE_BATCH, repeats=2):
     cores = os.cpu_count() or 1
     cpu_step(sample_batch, cores)                     # warm
     vals = [cpu_step(sample_batch, cores) for _ in range(repeats)]
     best = max(v for v, _ in vals)
-    return {"value": round(best, 8), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "six shape classes once each at B=%d (H=16, N=2048), torch CPU port of the reference "
-                      "composition (oracle/ct_torch.py), %d threads, %.1f s per pass" % (sample_batch, cores,
-                                                                                         vals[-1][1])}
+    kind = _reference_modules()["kind"]
+    return {"value": round(best, 8), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "the six shape classes once each at B=%d of the config's 32 (H=16, N=2048), %s, "
+                      "%d threads, %.1f s per pass" % (sample_batch,
+                                                      "the reference's own layers/cloud_transform.py (oracle/_ref)"
+                                                      if kind == "reference" else "torch port oracle/ct_torch.py",
+                                                      cores, vals[-1][1])}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (its torch composition; the
-    reference is Python and cannot travel, so the port in oracle/ct_torch.py stands in), all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path (its unmodified layers/cloud_transform.py
+    from the staged tree), all host threads, on a bounded sample of the SAME workload config: per step the six shape
+    classes once each at B=8 of the 32 clouds (the metric is per point-head, so the sample size cancels)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample_batch = 8
-    for _ in range(args.warmup):
-        cpu_step(sample_batch, cores)
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(CPU_SAMPLE_BATCH, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(sample_batch, cores)
+        cpu_step(CPU_SAMPLE_BATCH, cores)
     dt = (time.perf_counter() - t0) / args.steps
-    val = len(CLASSES) * sample_batch * H * N_PTS / dt / 1e9
+    val = len(CLASSES) * CPU_SAMPLE_BATCH * H * N_PTS / dt / 1e9
+    kind = _reference_modules()["kind"]
     line = {
         "impl": "reference", "metric": METRIC, "value": round(val, 8), "unit": UNIT,
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "scanobjectnn_hotpath", "heads": H, "points": N_PTS,
-                   "classes": [c[0] for c in CLASSES], "sample_batch": sample_batch},
-        "cpu_baseline": {"value": round(val, 8), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "six shape classes once each at B=%d per step" % sample_batch},
+        "config": workload_config(args.mode),
+        "cpu_baseline": {"value": round(val, 8), "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "per step: the six shape classes once each at B=%d of the config's 32 clouds, the "
+                                   "reference's own DifferentiablePositions / Splat / Slice forward + backward (scatter_max "
+                                   "through the shim of oracle/reference_loader.py)" % CPU_SAMPLE_BATCH},
         "e2e": {"value": round(val, 8), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -557,11 +802,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--train-steps", type=int, default=10, help="steps of the MHCT training throughput add-on (0 = skip)")
+    ap.add_argument("--train-steps", type=int, default=100, help="steps of the MHCT training throughput add-on (0 = skip)")
     ap.add_argument("--train-batch", type=int, default=B_PER_GPU)
     ap.add_argument("--grid-dtype", default="f32", choices=["f32", "bf16"],
                     help="bf16: grids (z, convolved, grad_grid, grad_z) stored as bf16, arithmetic stays fp32")
     ap.add_argument("--mode", default=os.environ.get("CTB_MODE", "auto"), choices=["auto", "atomic", "tile", "deterministic"])
+    ap.add_argument("--skip", default="", help="developer switch: comma list of add-on sections to skip "
+                                               "(e2e, refgpu, det, others, train, cpu, bf16)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

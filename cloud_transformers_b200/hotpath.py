@@ -63,8 +63,13 @@ class HotPath:
         n += 1                                                            # splat bwd
         return n
 
+    def _call(self, name, *args):
+        # kernels, stream and pointers must all belong to self.device, whatever the caller's current device is
+        with torch.cuda.device(self.device):
+            _call(name, *args)
+
     def build_plan(self, keys):
-        _call("ctb_plan_build", _ptr(keys), _ptr(self.plan), ctypes.c_size_t(self.plan.numel()), self._sh,
+        self._call("ctb_plan_build", _ptr(keys), _ptr(self.plan), ctypes.c_size_t(self.plan.numel()), self._sh,
               _stream(keys))
 
     def splat_fwd(self, keys, feat, pad=None):
@@ -73,22 +78,22 @@ class HotPath:
         return self.splat_fwd_only(keys, feat, pad)
 
     def splat_fwd_only(self, keys, feat, pad=None):
-        _call("ctb_splat_fwd_keys", _ptr(keys), _ptr(feat), _ptr(pad), _ptr(self.z), _ptr(self.arg), self._sh,
+        self._call("ctb_splat_fwd_keys", _ptr(keys), _ptr(feat), _ptr(pad), _ptr(self.z), _ptr(self.arg), self._sh,
               self.reduce, self.modes[_lib.OP_SPLAT_FWD], _ptr(self.plan), _stream(keys))
         return self.z
 
     def slice_fwd(self, keys, grid, pad=None):
-        _call("ctb_slice_fwd_keys", _ptr(keys), _ptr(grid), _ptr(pad), _ptr(self.out), self._sh,
+        self._call("ctb_slice_fwd_keys", _ptr(keys), _ptr(grid), _ptr(pad), _ptr(self.out), self._sh,
               self.modes[_lib.OP_SLICE_FWD], _stream(keys))
         return self.out
 
     def slice_bwd(self, keys, grid, grad_out, pad=None):
-        _call("ctb_slice_bwd_keys", _ptr(keys), _ptr(grid), _ptr(pad), _ptr(grad_out), _ptr(self.grad_grid),
+        self._call("ctb_slice_bwd_keys", _ptr(keys), _ptr(grid), _ptr(pad), _ptr(grad_out), _ptr(self.grad_grid),
               _ptr(self.grad_keys_slice), self._sh, self.modes[_lib.OP_SLICE_BWD], _ptr(self.plan), _stream(keys))
         return self.grad_grid, self.grad_keys_slice
 
     def splat_bwd(self, keys, feat, grad_z, pad=None):
-        _call("ctb_splat_bwd_keys", _ptr(keys), _ptr(feat), _ptr(pad), _ptr(grad_z), _ptr(self.arg),
+        self._call("ctb_splat_bwd_keys", _ptr(keys), _ptr(feat), _ptr(pad), _ptr(grad_z), _ptr(self.arg),
               _ptr(self.grad_feat), _ptr(self.grad_keys_splat), self._sh, self.reduce,
               self.modes[_lib.OP_SPLAT_BWD], _stream(keys))
         return self.grad_feat, self.grad_keys_splat
