@@ -61,6 +61,9 @@ SIGNATURES = {
     "ctb_project_fwd_stats": (_I, [_P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _SH, _P]),
     "ctb_project_bwd": (_I, [_P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _SH, _P]),
     "ctb_project_bwd_workspace_bytes": (ctypes.c_size_t, [_SH]),
+    "ctb_chamfer_workspace_bytes": (ctypes.c_size_t, [_I, _I, _I]),
+    "ctb_chamfer_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _I, _I, _I, _P]),
+    "ctb_chamfer_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "ctb_count_occupied": (_I, [_P, ctypes.c_uint64, _P, _P]),
 }
 

@@ -9,6 +9,7 @@
 #include "ctb_tile_cl.cuh"
 #include "ctb_binned.cuh"
 #include "ctb_project.cuh"
+#include "ctb_chamfer.cuh"
 
 namespace {
 
@@ -338,7 +339,10 @@ int ctb_mode_supported(const ctb_shape* shape, int op, int reduce, int mode) {
   switch (op) {
     case CTB_OP_SPLAT_FWD:
       return det ? binned_ok(shape) : (binned_in_tile(shape, sum) || ctb::tile_scatter_config(shape, sum, !sum, &tc));
-    case CTB_OP_SPLAT_BWD: return sum ? 0 : ctb::gather_config(shape, ctb::GATHER_SPLAT_BWD, &gc);
+    case CTB_OP_SPLAT_BWD:
+      return sum ? (ctb::gather_config(shape, ctb::GATHER_SLICE_FWD, &gc) &&
+                    ctb::gather_config(shape, ctb::GATHER_SLICE_BWD_KEYS, &gc))
+                 : ctb::gather_config(shape, ctb::GATHER_SPLAT_BWD, &gc);
     case CTB_OP_SLICE_FWD: return ctb::gather_config(shape, ctb::GATHER_SLICE_FWD, &gc);
     case CTB_OP_SLICE_BWD:
       return (det ? binned_ok(shape) : (binned_in_tile(shape, true) || ctb::tile_scatter_config(shape, true, false, &tc))) &&
@@ -406,7 +410,15 @@ int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pa
   if (reduce != CTB_REDUCE_MAX && reduce != CTB_REDUCE_SUM) return CTB_ERR_INVALID_ARGUMENT;
   if (reduce == CTB_REDUCE_MAX && !arg) return CTB_ERR_INVALID_ARGUMENT;
   if (mode == CTB_MODE_DETERMINISTIC || mode == CTB_MODE_TILE) {
-    if (reduce != CTB_REDUCE_MAX) return CTB_ERR_UNSUPPORTED;
+    if (reduce == CTB_REDUCE_SUM) {
+      // every entry contributes: grad_features is the Slice forward of grad_z, and the weight gradients are those of
+      // a Slice backward whose "grid" is grad_z and whose upstream gradient is the features -- both gathers exist
+      st = cuda_status(gather_dispatch<ctb::GATHER_SLICE_FWD>(keys, grad_z_any, nullptr, nullptr, pad, grad_features,
+                                                              nullptr, shape, (cudaStream_t)stream));
+      if (st) return st;
+      return cuda_status(gather_dispatch<ctb::GATHER_SLICE_BWD_KEYS>(keys, grad_z_any, nullptr, features, pad, nullptr,
+                                                                      grad_keys, shape, (cudaStream_t)stream));
+    }
     return cuda_status(gather_dispatch<ctb::GATHER_SPLAT_BWD>(keys, grad_z_any, arg, features, pad, grad_features,
                                                                grad_keys, shape, (cudaStream_t)stream));
   }
@@ -520,6 +532,32 @@ size_t ctb_project_bwd_workspace_bytes(const ctb_shape* shape) {
   if (check_shape(shape, false)) return 0;
   const size_t chunks = (size_t)(shape->N + 31) / 32;
   return (size_t)shape->B * chunks * shape->H * ctb::kProjAcc * sizeof(float);
+}
+
+size_t ctb_chamfer_workspace_bytes(int B, int n, int m) {
+  if (B <= 0 || n <= 0 || m <= 0) return 0;
+  return ((size_t)B * n + (size_t)B * m) * sizeof(unsigned long long);
+}
+
+int ctb_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
+                    void* workspace, size_t workspace_bytes, int B, int n, int m, void* stream) {
+  if (B <= 0 || n <= 0 || m <= 0) return CTB_ERR_INVALID_ARGUMENT;
+  if (!xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return CTB_ERR_INVALID_ARGUMENT;
+  if (!workspace || workspace_bytes < ctb_chamfer_workspace_bytes(B, n, m)) return CTB_ERR_WORKSPACE;
+  if (B > 65535) return CTB_ERR_UNSUPPORTED;
+  return cuda_status(ctb::chamfer_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, (unsigned long long*)workspace, B, n, m,
+                                          (cudaStream_t)stream));
+}
+
+int ctb_chamfer_bwd(const float* xyz1, const float* xyz2, const float* grad_dist1, const float* grad_dist2,
+                    const int32_t* idx1, const int32_t* idx2, float* grad_xyz1, float* grad_xyz2, int B, int n, int m,
+                    void* stream) {
+  if (B <= 0 || n <= 0 || m <= 0) return CTB_ERR_INVALID_ARGUMENT;
+  if (!xyz1 || !xyz2 || !grad_dist1 || !grad_dist2 || !idx1 || !idx2 || !grad_xyz1 || !grad_xyz2)
+    return CTB_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return CTB_ERR_UNSUPPORTED;
+  return cuda_status(ctb::chamfer_backward(xyz1, xyz2, grad_dist1, grad_dist2, idx1, idx2, grad_xyz1, grad_xyz2, B, n, m,
+                                           (cudaStream_t)stream));
 }
 
 int ctb_count_occupied(const float* z, uint64_t n_elements, unsigned long long* count, void* stream) {

@@ -179,6 +179,21 @@ size_t ctb_project_bwd_workspace_bytes(const ctb_shape* shape);
  * accumulated into *count (u64, device memory, caller zeroes it). */
 int ctb_count_occupied(const float* z, uint64_t n_elements, unsigned long long* count, void* stream);
 
+/* ---- N3: Chamfer nearest-neighbour distances (the completion loss, train_inpainter.py:190) ------------------------ */
+/* Replaces chamfer_extension/chamfer.cu:136-153 chamfer_cuda_forward (NmDistanceKernel :12-134) as bound by
+ * chamfer_extension/dist_chamfer.py:10-38:  dist1[b,j] = min_k |xyz1[b,j] - xyz2[b,k]|^2, idx1 = the FIRST minimising k
+ * (ascending k, strict <), and the same with the clouds swapped.  xyz1 f32 [B,n,3], xyz2 f32 [B,m,3] (contiguous),
+ * dist f32, idx i32.  workspace: ctb_chamfer_workspace_bytes(B, n, m) bytes of device scratch. */
+size_t ctb_chamfer_workspace_bytes(int B, int n, int m);
+int ctb_chamfer_fwd(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int32_t* idx1, int32_t* idx2,
+                    void* workspace, size_t workspace_bytes, int B, int n, int m, void* stream);
+/* Replaces chamfer_cuda_backward (chamfer.cu:176-195, NmDistanceGradKernel :155-174): grad_xyz1 / grad_xyz2 are fully
+ * overwritten (zeroed, then accumulated with atomics like the reference: g = 2 grad_dist, +g (p1 - p2) on the query,
+ * -g (p1 - p2) on its nearest neighbour). */
+int ctb_chamfer_bwd(const float* xyz1, const float* xyz2, const float* grad_dist1, const float* grad_dist2,
+                    const int32_t* idx1, const int32_t* idx2, float* grad_xyz1, float* grad_xyz2, int B, int n, int m,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

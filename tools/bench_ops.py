@@ -22,6 +22,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--mode", default="auto")
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--batch", type=int, default=bench.B_PER_GPU)
+ap.add_argument("--pairs", action="store_true", help="also time the 2-D / 3-D class pairs on two streams")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 peak, _ = bench.peak_hbm()
@@ -72,3 +73,44 @@ for name, dim, W, F in bench.CLASSES:
         err = (gg1.float() - hp.grad_grid.float()).abs().max().item() / max(1e-30, hp.grad_grid.float().abs().max().item())
         print("%s check: z %s arg %s grad_grid max rel err %.2e" % (name, ok_z, ok_a, err))
 print("class set total %.4f ms -> step %.3f ms" % (tot, tot * bench.REPEATS))
+
+
+if args.pairs:
+    # the 2-D and the 3-D head of a MultiHeadUnion are independent (layers/multihead_ct.py:191-194): run their passes on
+    # two streams and compare with back-to-back execution on one
+    gen = torch.Generator(device=dev).manual_seed(42)
+    cls = {c[0]: c for c in bench.CLASSES}
+    for a, b in (("a2d", "a3d"), ("b2d", "b3d"), ("c2d", "c3d")):
+        items = []
+        for name in (a, b):
+            _, dim, W, F = cls[name]
+            items.append((HotPath(W, bench.H, dim, args.batch, F, bench.N_PTS, dev, mode=args.mode),
+                          bench.make_class_inputs(gen, dim, W, F, args.batch, dev)))
+        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+
+        def seq():
+            for hp, d in items:
+                hp.fwd_bwd(*d)
+
+        def par():
+            main = torch.cuda.current_stream()
+            for st, (hp, d) in zip(streams, items):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    hp.fwd_bwd(*d)
+            for st in streams:
+                main.wait_stream(st)
+
+        for fn, label in ((seq, "one stream"), (par, "two streams")):
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(args.reps):
+                bench.flush_l2(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            print("%s+%s %-11s %.4f ms" % (a, b, label, statistics.median(ts)))
