@@ -51,6 +51,7 @@ SIGNATURES = {
     "ctb_slice_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _SH, _P]),
     "ctb_mode_supported": (_I, [_SH, _I, _I, _I]),
     "ctb_plan_used": (_I, [_SH, _I]),
+    "ctb_op_uses_plan": (_I, [_SH, _I, _I, _I]),
     "ctb_plan_bytes": (ctypes.c_size_t, [_SH]),
     "ctb_plan_build": (_I, [_P, _P, ctypes.c_size_t, _SH, _P]),
     "ctb_splat_fwd_keys": (_I, [_P, _P, _P, _P, _P, _SH, _I, _I, _P, _P]),

@@ -357,6 +357,15 @@ int ctb_plan_used(const ctb_shape* shape, int mode) {
   return (mode == CTB_MODE_DETERMINISTIC ? binned_ok(shape) : binned_in_tile(shape, true)) ? 1 : 0;
 }
 
+int ctb_op_uses_plan(const ctb_shape* shape, int op, int reduce, int mode) {
+  if (check_shape(shape, true)) return 0;
+  if (op != CTB_OP_SPLAT_FWD && op != CTB_OP_SLICE_BWD) return 0;          // the gathers never read it
+  const bool sum = op == CTB_OP_SLICE_BWD || reduce == CTB_REDUCE_SUM;
+  if (mode == CTB_MODE_DETERMINISTIC) return binned_ok(shape) ? 1 : 0;
+  if (mode == CTB_MODE_TILE) return binned_in_tile(shape, sum) ? 1 : 0;
+  return 0;
+}
+
 size_t ctb_plan_bytes(const ctb_shape* shape) {
   if (check_shape(shape, false)) return 0;
   if (!ctb::plan_supported(shape)) return 0;

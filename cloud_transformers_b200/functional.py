@@ -205,6 +205,7 @@ class PositionsHandle:
         self.geom = geom
         self._keys_c = None
         self._plan = None
+        self._plan_event = None
 
     def keys_c(self):
         if self._keys_c is None:
@@ -237,20 +238,62 @@ class PositionsHandle:
             return None
         return self.plan()
 
+    def _build_plan(self):
+        k = self.keys_c()
+        B, _, N = k.shape
+        sh = self.geom.shape(B, 1, N)
+        lib = _lib.load()
+        nbytes = lib.ctb_plan_bytes(ctypes.byref(sh))
+        if nbytes == 0:
+            raise _lib.CtbError("ctb_plan_bytes", _lib.CTB_ERR_UNSUPPORTED, "shape cannot be planned")
+        plan = torch.empty(nbytes, dtype=torch.uint8, device=k.device)
+        with torch.cuda.device(k.device):
+            _call("ctb_plan_build", _ptr(k), _ptr(plan), ctypes.c_size_t(nbytes), ctypes.byref(sh), _stream(k))
+        return plan
+
     def plan(self):
         if self._plan is None:
-            k = self.keys_c()
-            B, _, N = k.shape
-            sh = self.geom.shape(B, 1, N)
-            lib = _lib.load()
-            nbytes = lib.ctb_plan_bytes(ctypes.byref(sh))
-            if nbytes == 0:
-                raise _lib.CtbError("ctb_plan_bytes", _lib.CTB_ERR_UNSUPPORTED, "shape cannot be planned")
-            plan = torch.empty(nbytes, dtype=torch.uint8, device=k.device)
-            with torch.cuda.device(k.device):
-                _call("ctb_plan_build", _ptr(k), _ptr(plan), ctypes.c_size_t(nbytes), ctypes.byref(sh), _stream(k))
-            self._plan = plan
+            self._plan = self._build_plan()
+        elif self._plan_event is not None:
+            # built ahead on the side stream (prefetch_plan): order this stream behind it, once
+            cur = torch.cuda.current_stream(self._plan.device)
+            cur.wait_event(self._plan_event)
+            self._plan.record_stream(cur)
+            self._plan_event = None
         return self._plan
+
+    def prefetch_plan(self, mode, F):
+        """Splat forward calls this when the plan is only read later (the grad_grid sum of Slice backward on grids
+        whose forward max keeps the tile scatter): build it on a side stream under the forward passes instead of on
+        the backward's critical path.  Skipped under CUDA-graph capture (a fork that a forward-only capture never joins)."""
+        if self._plan is not None or not config.use_plan or not torch.is_grad_enabled():
+            return
+        k = self.keys
+        if torch.cuda.is_current_stream_capturing():
+            return
+        sh = self.geom.shape(k.size(0), F, k.size(-1))
+        lib = _lib.load()
+        if not lib.ctb_plan_used(ctypes.byref(sh), mode) or lib.ctb_op_uses_plan(ctypes.byref(sh), _lib.OP_SPLAT_FWD, 0, mode):
+            return
+        kc = self.keys_c()
+        cur = torch.cuda.current_stream(kc.device)
+        side = _side_stream(kc.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._plan = self._build_plan()
+            self._plan_event = torch.cuda.Event()
+            self._plan_event.record(side)
+        kc.record_stream(side)
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
 
 
 def _grid_dtype_code(dtype, mode):
@@ -271,7 +314,9 @@ class _FusedSplatFn(torch.autograd.Function):
         B, N = f_c.size(0), f_c.size(-1)
         F = f_c.size(1) // geom.heads
         mode = handle.mode_for(_lib.OP_SPLAT_FWD, F, reduce)
-        plan = handle.plan_for(mode, F)
+        uses_plan = mode != _lib.MODE_ATOMIC and _lib.load().ctb_op_uses_plan(
+            ctypes.byref(geom.shape(B, F, N)), _lib.OP_SPLAT_FWD, reduce, mode)
+        plan = handle.plan_for(mode, F) if uses_plan else None
         gd = _grid_dtype_code(out_dtype, mode)
         ctx.gd = gd
         z = torch.empty((B, geom.heads * F) + geom.sizes,
@@ -283,6 +328,8 @@ class _FusedSplatFn(torch.autograd.Function):
                   ctypes.byref(geom.shape(B, F, N, gd)), reduce, mode, _ptr(plan), _stream(f_c))
         ctx.save_for_backward(k, f_c, p_c, arg)
         ctx.handle, ctx.reduce = handle, reduce
+        if plan is None and mode == _lib.MODE_TILE and (features.requires_grad or keys.requires_grad):
+            handle.prefetch_plan(mode, F)
         if out_dtype is not None and z.dtype != out_dtype:
             z = z.to(out_dtype)
         return z

@@ -135,6 +135,10 @@ int ctb_mode_supported(const ctb_shape* shape, int op, int reduce, int mode);
  * ctb_plan_used: 1 if the kernels of `mode` use a plan on this shape (then the caller should build one and pass it;
  * DETERMINISTIC requires it, TILE falls back to its shared-memory tile scatters when plan == NULL). */
 int ctb_plan_used(const ctb_shape* shape, int mode);
+/* 1 if `op` (CTB_OP_SPLAT_FWD with `reduce`, or CTB_OP_SLICE_BWD) reads the plan in `mode` on this shape.  Lets a
+ * caller build the plan off the critical path when only the backward needs it (16^3 x F16: the forward max keeps the
+ * tile scatter, the grad_grid sum of Slice backward is plan-based). */
+int ctb_op_uses_plan(const ctb_shape* shape, int op, int reduce, int mode);
 /* bytes of the plan for this shape, 0 if the shape cannot be planned. */
 size_t ctb_plan_bytes(const ctb_shape* shape);
 int ctb_plan_build(const float* keys, void* plan, size_t plan_bytes, const ctb_shape* shape, void* stream);
