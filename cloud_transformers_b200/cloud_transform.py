@@ -66,9 +66,11 @@ def _handle_of(local_coordinate, flattened_index):
     tag = getattr(local_coordinate, "_ctb_tag", None)
     if tag is None or getattr(flattened_index, "_ctb_tag", None) is not tag:
         return None
-    handle, lc_version, idx_version = tag
+    handle, lc_version, idx_version, keys_version = tag
     if local_coordinate._version != lc_version or flattened_index._version != idx_version:
         return None  # modified in place since we produced them
+    if handle.keys._version != keys_version:
+        return None  # the keys were modified in place: lc / idx still describe the old positions, use them as given
     return handle
 
 
@@ -88,7 +90,7 @@ class DifferentiablePositions(DifferentiableGridModule):
             return (keys.new_zeros((B, self.heads, S, N)) + 0.0 * keys.sum(),
                     torch.zeros((B, self.heads, S, N), dtype=torch.int64, device=keys.device))
         local_coordinate, flattened_index = CF.positions(keys, self._geom)
-        tag = (CF.PositionsHandle(keys, self._geom), local_coordinate._version, flattened_index._version)
+        tag = (CF.PositionsHandle(keys, self._geom), local_coordinate._version, flattened_index._version, keys._version)
         local_coordinate._ctb_tag = tag
         flattened_index._ctb_tag = tag
         return local_coordinate, flattened_index

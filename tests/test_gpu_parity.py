@@ -592,3 +592,25 @@ def test_bf16_grid_storage_mode(shape):
     (z.float() * t(gz)).sum().backward()
     assert_close(n(f.grad), ref["gfeat"], "grad features", rtol=1e-2, atol_scale=1e-2)
     assert_close(n(k.grad), ref["gk_splat"], "grad keys via splat", rtol=1e-2, atol_scale=1e-2)
+
+
+def test_fused_path_is_dropped_when_keys_change_in_place():
+    """lc / idx describe the positions at the time DifferentiablePositions ran (the reference's Splat / Slice only see
+    those tensors): if the keys are modified in place afterwards, the fused path -- which would recompute the positions
+    from the new keys -- must not be taken."""
+    dim, W, H, F, N, B = 2, 16, 2, 4, 300, 2
+    keys, feat, _ = make_inputs(3, B, H, dim, F, N)
+    dp = ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim).to(DEV)
+    sp = ctb.Splat(tensor_size=W, heads=H, dim=dim).to(DEV)
+    sl = ctb.Slice(tensor_size=W, heads=H, dim=dim).to(DEV)
+    with torch.no_grad():
+        k = t(keys)
+        lc, idx = dp(k)
+        z_before = sp(lc, idx, t(feat))
+        k.mul_(-0.5)                                   # in-place change of the keys after the positions were taken
+        z_after = sp(lc, idx, t(feat))
+        out_after = sl(lc, idx, z_after)
+    lc_o, idx_o = O.positions_fwd(keys, W, H, dim)
+    z_o = O.splat_fwd(lc_o, idx_o, feat, W, H, dim)
+    assert np.array_equal(n(z_before), z_o) and np.array_equal(n(z_after), z_o)
+    assert_close(n(out_after), O.slice_fwd(lc_o, idx_o, z_o, H), "slice after in-place key change")
