@@ -614,3 +614,43 @@ def test_fused_path_is_dropped_when_keys_change_in_place():
     z_o = O.splat_fwd(lc_o, idx_o, feat, W, H, dim)
     assert np.array_equal(n(z_before), z_o) and np.array_equal(n(z_after), z_o)
     assert_close(n(out_after), O.slice_fwd(lc_o, idx_o, z_o, H), "slice after in-place key change")
+
+
+@pytest.mark.parametrize("shape", FULL + BIG, ids=lambda s: "d%d_w%d_h%d_f%d_n%d_b%d" % s)
+def test_full_and_big_shapes_one_unit_against_oracle_with_gradients(shape):
+    """Every BASELINE-size shape, default algorithm: forward AND all four gradients of one (b, h) unit against the
+    oracle.  Units are independent (each owns its grid slab, cloud_transform.py:164-178), so the oracle only has to run
+    on the slice of the inputs that unit sees; the unit is taken from the middle of the batch and the heads."""
+    dim, W, H, F, N, B = shape
+    g = torch.Generator(device=DEV).manual_seed(11)
+    keys = torch.tanh(torch.randn(B, H * dim, N, device=DEV, generator=g))
+    feat = torch.randn(B, H * F, N, device=DEV, generator=g)
+    grid = (B, H * F) + (W,) * dim
+    conv = torch.randn(grid, device=DEV, generator=g)
+    go = torch.randn(B, H * F, N, device=DEV, generator=g)
+    gz = torch.randn(grid, device=DEV, generator=g)
+    ctb.config.mode = "auto"
+    dp = ctb.DifferentiablePositions(tensor_size=W, heads=H, dim=dim)
+    sp = ctb.Splat(tensor_size=W, heads=H, dim=dim)
+    sl = ctb.Slice(tensor_size=W, heads=H, dim=dim)
+    k = keys.clone().requires_grad_(True)
+    f = feat.clone().requires_grad_(True)
+    c = conv.clone().requires_grad_(True)
+    lc, idx = dp(k)
+    z = sp(lc, idx, f)
+    out = sl(lc, idx, c)
+    gk_slice, gconv = torch.autograd.grad((out * go).sum(), [k, c], retain_graph=True)
+    gk_splat, gfeat = torch.autograd.grad((z * gz).sum(), [k, f])
+    b, h = B // 2, H // 2
+    ks = slice(h * dim, (h + 1) * dim)
+    fs = slice(h * F, (h + 1) * F)
+    ref = oracle_block(n(keys[b:b + 1, ks]), n(feat[b:b + 1, fs]), None, n(conv[b:b + 1, fs]), n(go[b:b + 1, fs]),
+                       n(gz[b:b + 1, fs]), W, 1, dim)
+    what = "unit (%d, %d) of %s" % (b, h, (shape,))
+    assert np.array_equal(n(idx[b:b + 1, h:h + 1]), ref["idx"]) and np.array_equal(n(lc[b:b + 1, h:h + 1]), ref["lc"])
+    assert np.array_equal(n(z[b:b + 1, fs]), ref["z"]), what + ": Splat-max grid must be bit-exact"
+    assert_close(n(out[b:b + 1, fs]), ref["out"], what + " out")
+    assert_close(n(gconv[b:b + 1, fs]), ref["gconv"], what + " grad grid")
+    assert_close(n(gfeat[b:b + 1, fs]), ref["gfeat"], what + " grad features")
+    assert_close(n(gk_slice[b:b + 1, ks]), ref["gk_slice"], what + " grad keys (Slice)")
+    assert_close(n(gk_splat[b:b + 1, ks]), ref["gk_splat"], what + " grad keys (Splat)")
