@@ -10,6 +10,7 @@
 #include "ctb_binned.cuh"
 #include "ctb_project.cuh"
 #include "ctb_chamfer.cuh"
+#include "ctb_syncbn.cuh"
 
 namespace {
 
@@ -567,6 +568,52 @@ int ctb_chamfer_bwd(const float* xyz1, const float* xyz2, const float* grad_dist
   if (B > 65535) return CTB_ERR_UNSUPPORTED;
   return cuda_status(ctb::chamfer_backward(xyz1, xyz2, grad_dist1, grad_dist2, idx1, idx2, grad_xyz1, grad_xyz2, B, n, m,
                                            (cudaStream_t)stream));
+}
+
+static int bn_exchange_of(const ctb_bn_exchange* ex, int C, ctb::BnExchange* out) {
+  if (!ex || !ex->peer_data || !ex->peer_flag || !ex->epoch || !ex->done) return CTB_ERR_INVALID_ARGUMENT;
+  if (ex->world < 1 || ex->world > 32 || ex->rank < 0 || ex->rank >= ex->world) return CTB_ERR_INVALID_ARGUMENT;
+  out->peer_data = (float* const*)ex->peer_data;
+  out->peer_flag = (unsigned* const*)ex->peer_flag;
+  out->epoch = ex->epoch;
+  out->done = ex->done;
+  out->rank = ex->rank;
+  out->world = ex->world;
+  out->C = C;
+  return CTB_OK;
+}
+
+int ctb_syncbn_fwd(const float* x, const float* weight, const float* bias, float* y, float* save_mean, float* save_invstd,
+                   float* running_mean, float* running_var, const ctb_bn_exchange* exchange, int B, int C, int L, float eps,
+                   float momentum, void* stream) {
+  if (!x || !y || !save_mean || !save_invstd || B <= 0 || C <= 0 || L <= 0) return CTB_ERR_INVALID_ARGUMENT;
+  ctb::BnExchange ex;
+  int st = bn_exchange_of(exchange, C, &ex);
+  if (st) return st;
+  const int chunks = ctb::bn_chunks(C, (long long)B * L);
+  ctb::syncbn_fwd_stats_kernel<<<C, ctb::kBnThreads, 0, (cudaStream_t)stream>>>(x, ex, B, L);
+  CTB_LAUNCH_CHECK();
+  ctb::syncbn_fwd_apply_kernel<<<dim3(C, chunks), ctb::kBnThreads, 0, (cudaStream_t)stream>>>(
+      x, weight, bias, y, save_mean, save_invstd, running_mean, running_var, ex, B, L, eps, momentum);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+int ctb_syncbn_bwd(const float* x, const float* grad_y, const float* weight, const float* save_mean, const float* save_invstd,
+                   float* grad_x, float* grad_weight, float* grad_bias, const ctb_bn_exchange* exchange, int B, int C, int L,
+                   void* stream) {
+  if (!x || !grad_y || !save_mean || !save_invstd || !grad_x || B <= 0 || C <= 0 || L <= 0) return CTB_ERR_INVALID_ARGUMENT;
+  ctb::BnExchange ex;
+  int st = bn_exchange_of(exchange, C, &ex);
+  if (st) return st;
+  const int chunks = ctb::bn_chunks(C, (long long)B * L);
+  ctb::syncbn_bwd_stats_kernel<<<C, ctb::kBnThreads, 0, (cudaStream_t)stream>>>(x, grad_y, save_mean, save_invstd, grad_weight,
+                                                                               grad_bias, ex, B, L);
+  CTB_LAUNCH_CHECK();
+  ctb::syncbn_bwd_apply_kernel<<<dim3(C, chunks), ctb::kBnThreads, 0, (cudaStream_t)stream>>>(x, grad_y, weight, save_mean,
+                                                                                          save_invstd, grad_x, ex, B, L);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
 }
 
 int ctb_count_occupied(const float* z, uint64_t n_elements, unsigned long long* count, void* stream) {

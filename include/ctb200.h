@@ -198,6 +198,35 @@ int ctb_chamfer_bwd(const float* xyz1, const float* xyz2, const float* grad_dist
                     const int32_t* idx1, const int32_t* idx2, float* grad_xyz1, float* grad_xyz2, int B, int n, int m,
                     void* stream);
 
+/* ---- N2: SyncBatchNorm with the cross-GPU exchange fused into its kernels (train_classification.py:107-109) -------- */
+/* Replaces torch.nn.SyncBatchNorm's statistics kernel -> NCCL all_gather / all_reduce -> combine -> elementwise chain
+ * (106 layers = 212 small collectives per step in model_zoo/scanobject/classifier.py) by two kernels per direction whose
+ * exchange is a one-shot all-gather over NVLink peer memory: the statistics kernel stores its per-channel partial sums
+ * straight into the exchange block of every rank and publishes an epoch flag; the elementwise kernel waits for the flags
+ * of all ranks and sums the partials in rank order (identical bits on every rank).
+ *   exchange block of one layer and direction, on EVERY rank in peer-mapped (symmetric) memory, zero-initialised:
+ *       data f32 [2][world][2*C] followed anywhere by flag u32 [2][world]
+ *   peer_data / peer_flag: DEVICE arrays of `world` pointers to that block's data / flag part on each rank;
+ *   epoch u32 [1], done u32 [2]: ordinary device memory of this rank, zero-initialised, owned by this layer + direction.
+ * Equal B and L on every rank.  x, y, grad_y, grad_x: f32 [B, C, L] contiguous. */
+typedef struct ctb_bn_exchange {
+  void* const* peer_data;
+  void* const* peer_flag;
+  uint32_t* epoch;
+  uint32_t* done;
+  int32_t rank;
+  int32_t world;
+} ctb_bn_exchange;
+/* training-mode forward: y, save_mean / save_invstd f32 [C] (for the backward), running statistics updated in place
+ * (may be NULL) with momentum and the unbiased variance, like nn.SyncBatchNorm. */
+int ctb_syncbn_fwd(const float* x, const float* weight, const float* bias, float* y, float* save_mean, float* save_invstd,
+                   float* running_mean, float* running_var, const ctb_bn_exchange* exchange, int B, int C, int L, float eps,
+                   float momentum, void* stream);
+/* backward: grad_x; grad_weight / grad_bias f32 [C] are this rank's LOCAL sums (DDP reduces parameter gradients). */
+int ctb_syncbn_bwd(const float* x, const float* grad_y, const float* weight, const float* save_mean, const float* save_invstd,
+                   float* grad_x, float* grad_weight, float* grad_bias, const ctb_bn_exchange* exchange, int B, int C, int L,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
