@@ -334,7 +334,7 @@ def run_ours(args):
     torch.cuda.empty_cache()
     others = run_other_configs(args, dev) if (rank == 0 and "others" not in skip) else None
     barrier()
-    train = train_eager = None
+    train = train_eager = train_fused = None
     if args.train_steps > 0 and "train" not in skip:
         train_eager = run_train(args, dev, world, rank, graphed=False)
         torch.cuda.empty_cache()
@@ -342,6 +342,10 @@ def run_ours(args):
         train = run_train(args, dev, world, rank, graphed=True)
         if "unavailable" in train:          # capture failed: the eager loop is the number
             train, train_eager = train_eager, train
+        if world > 1 and "fusedbn" not in skip:
+            torch.cuda.empty_cache()
+            barrier()
+            train_fused = run_train(args, dev, world, rank, graphed=True, fused_syncbn=True)
 
     if rank == 0:
         cpu = cpu_baseline() if "cpu" not in skip else None
@@ -363,6 +367,7 @@ def run_ours(args):
             "e2e": e2e,
             "train": train,
             "train_eager": train_eager,
+            "train_fused_syncbn": train_fused,
             "gpu_launches": n_launches,
             "clocks": clocks,
             "cpu_baseline": cpu,
@@ -616,7 +621,7 @@ def reference_composition_on_gpu(dev, data):
         torch.cuda.empty_cache()
 
 
-def run_train(args, dev, world, rank, graphed):
+def run_train(args, dev, world, rank, graphed, fused_syncbn=False):
     """Second half of the BASELINE metric: MHCT training samples/s on the reference's OWN ScanObjectNN classifier
     (model_zoo/scanobject/classifier.py, 24.02 M parameters) running on the B200 kernels through dropin/.  The loop is
     train_classification.py:181-273 on synthetic clouds (configs/scanobjectnn.yaml: Adam 1e-3, StepLR, seg_weight 0.5):
@@ -625,12 +630,17 @@ def run_train(args, dev, world, rank, graphed):
     all_gather of predictions (:37-77), the reference's own unmodified functions -- and the .item() reads of the losses
     and of the 26 x 3 lattice statistics rank 0 logs (:249-260).  Clouds come from pinned host memory every step.
     graphed=True: forward + backward + optimizer step (SyncBN / DDP collectives included) replay as ONE CUDA graph
-    (cloud_transformers_b200/graphed.py); the bookkeeping stays eager, after the replay."""
+    (cloud_transformers_b200/graphed.py); the bookkeeping stays eager, after the replay.
+    fused_syncbn=True: cloud_transformers_b200.syncbn.convert_sync_batchnorm instead of torch's -- same layers, same
+    state_dict, the per-layer statistics exchange done by the normalisation kernels themselves over NVLink peer memory
+    (csrc/ctb_syncbn.cuh) instead of one NCCL all_gather / all_reduce per layer and direction."""
     import torch
     import torch.distributed as dist
     from cloud_transformers_b200.graphed import GraphedTrainStep
     from cloud_transformers_b200.sharding import aggregate_throughput
+    from cloud_transformers_b200 import syncbn as ctb_syncbn
     try:
+        to_sync = ctb_syncbn.convert_sync_batchnorm if fused_syncbn else torch.nn.SyncBatchNorm.convert_sync_batchnorm
         torch.manual_seed(42)                          # train_classification.py:96
         torch.backends.cudnn.benchmark = True          # :58
         B = args.train_batch
@@ -642,8 +652,8 @@ def run_train(args, dev, world, rank, graphed):
         if world > 1:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):              # (the graph recipe wants DDP built on the warm-up stream)
-                model = torch.nn.parallel.DistributedDataParallel(torch.nn.SyncBatchNorm.convert_sync_batchnorm(model),
-                                                                  device_ids=[dev.index], output_device=dev.index)
+                model = torch.nn.parallel.DistributedDataParallel(to_sync(model), device_ids=[dev.index],
+                                                                  output_device=dev.index)
             torch.cuda.current_stream().wait_stream(side)
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0, capturable=graphed)
         sched = torch.optim.lr_scheduler.StepLR(opt, gamma=0.7, step_size=25000)
@@ -714,7 +724,10 @@ def run_train(args, dev, world, rank, graphed):
                         "all_gather + .item() logging every step",
                 "step_execution": "one CUDA graph per step (forward + backward + optimizer + SyncBN / DDP collectives), "
                                   "bookkeeping eager" if graphed else "eager, as the script",
-                "parallelism": "dp%d (DDP + SyncBN over NCCL)" % world if world > 1 else "single GPU"}
+                "syncbn": None if world == 1 else ("cloud_transformers_b200.syncbn: statistics exchanged by the "
+                                                   "normalisation kernels over NVLink peer memory" if fused_syncbn
+                                                   else "torch.nn.SyncBatchNorm (NCCL collective per layer and direction)"),
+                "parallelism": "dp%d (DDP over NCCL + SyncBN)" % world if world > 1 else "single GPU"}
     except Exception as exc:
         import traceback
         return {"unavailable": repr(exc)[:300], "trace": traceback.format_exc()[-900:]}

@@ -30,7 +30,8 @@ class CtbShape(ctypes.Structure):
 
 class CtbBnExchange(ctypes.Structure):
     _fields_ = [("peer_data", ctypes.c_void_p), ("peer_flag", ctypes.c_void_p), ("epoch", ctypes.c_void_p),
-                ("done", ctypes.c_void_p), ("rank", ctypes.c_int32), ("world", ctypes.c_int32)]
+                ("done", ctypes.c_void_p), ("scratch", ctypes.c_void_p), ("rank", ctypes.c_int32),
+                ("world", ctypes.c_int32)]
 
 
 class CtbError(RuntimeError):
@@ -70,6 +71,7 @@ SIGNATURES = {
     "ctb_chamfer_workspace_bytes": (ctypes.c_size_t, [_I, _I, _I]),
     "ctb_chamfer_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _I, _I, _I, _P]),
     "ctb_chamfer_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "ctb_syncbn_scratch_bytes": (ctypes.c_uint64, [_I]),
     "ctb_syncbn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(CtbBnExchange), _I, _I, _I, ctypes.c_float,
                             ctypes.c_float, _P]),
     "ctb_syncbn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(CtbBnExchange), _I, _I, _I, _P]),

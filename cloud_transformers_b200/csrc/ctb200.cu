@@ -1,5 +1,6 @@
 // ctb200.cu -- C ABI of libctb200.so (declared in include/ctb200.h).  sm_100a only.
 #include <cuda_runtime.h>
+#include <initializer_list>
 #include <stdint.h>
 #include "../../include/ctb200.h"
 #include "ctb_positions.cuh"
@@ -571,16 +572,28 @@ int ctb_chamfer_bwd(const float* xyz1, const float* xyz2, const float* grad_dist
 }
 
 static int bn_exchange_of(const ctb_bn_exchange* ex, int C, ctb::BnExchange* out) {
-  if (!ex || !ex->peer_data || !ex->peer_flag || !ex->epoch || !ex->done) return CTB_ERR_INVALID_ARGUMENT;
+  if (!ex || !ex->peer_data || !ex->peer_flag || !ex->epoch || !ex->done || !ex->scratch) return CTB_ERR_INVALID_ARGUMENT;
   if (ex->world < 1 || ex->world > 32 || ex->rank < 0 || ex->rank >= ex->world) return CTB_ERR_INVALID_ARGUMENT;
   out->peer_data = (float* const*)ex->peer_data;
   out->peer_flag = (unsigned* const*)ex->peer_flag;
   out->epoch = ex->epoch;
   out->done = ex->done;
+  out->scratch = (float2*)ex->scratch;
   out->rank = ex->rank;
   out->world = ex->world;
   out->C = C;
   return CTB_OK;
+}
+
+static bool bn_vec4(int L, std::initializer_list<const void*> ptrs) {
+  if (L % 4) return false;
+  for (const void* p : ptrs)
+    if ((uintptr_t)p & 15u) return false;
+  return true;
+}
+
+uint64_t ctb_syncbn_scratch_bytes(int C) {
+  return C > 0 ? (uint64_t)C * (ctb::kBnMaxChunks * sizeof(float2) + sizeof(unsigned)) : 0;
 }
 
 int ctb_syncbn_fwd(const float* x, const float* weight, const float* bias, float* y, float* save_mean, float* save_invstd,
@@ -590,11 +603,18 @@ int ctb_syncbn_fwd(const float* x, const float* weight, const float* bias, float
   ctb::BnExchange ex;
   int st = bn_exchange_of(exchange, C, &ex);
   if (st) return st;
-  const int chunks = ctb::bn_chunks(C, (long long)B * L);
-  ctb::syncbn_fwd_stats_kernel<<<C, ctb::kBnThreads, 0, (cudaStream_t)stream>>>(x, ex, B, L);
-  CTB_LAUNCH_CHECK();
-  ctb::syncbn_fwd_apply_kernel<<<dim3(C, chunks), ctb::kBnThreads, 0, (cudaStream_t)stream>>>(
-      x, weight, bias, y, save_mean, save_invstd, running_mean, running_var, ex, B, L, eps, momentum);
+  const long long per = (long long)B * L;
+  const dim3 gs(C, ctb::bn_chunks(C, per, ctb::kBnMaxChunks, 8192)), ga(C, ctb::bn_chunks(C, per, 65535, 4096));
+  cudaStream_t sm = (cudaStream_t)stream;
+  if (bn_vec4(L, {x, y})) {
+    ctb::syncbn_fwd_stats_kernel<4><<<gs, ctb::kBnThreads, 0, sm>>>(x, ex, B, L);
+    ctb::syncbn_fwd_apply_kernel<4><<<ga, ctb::kBnThreads, 0, sm>>>(x, weight, bias, y, save_mean, save_invstd, running_mean,
+                                                                    running_var, ex, B, L, eps, momentum);
+  } else {
+    ctb::syncbn_fwd_stats_kernel<1><<<gs, ctb::kBnThreads, 0, sm>>>(x, ex, B, L);
+    ctb::syncbn_fwd_apply_kernel<1><<<ga, ctb::kBnThreads, 0, sm>>>(x, weight, bias, y, save_mean, save_invstd, running_mean,
+                                                                    running_var, ex, B, L, eps, momentum);
+  }
   CTB_LAUNCH_CHECK();
   return CTB_OK;
 }
@@ -606,12 +626,18 @@ int ctb_syncbn_bwd(const float* x, const float* grad_y, const float* weight, con
   ctb::BnExchange ex;
   int st = bn_exchange_of(exchange, C, &ex);
   if (st) return st;
-  const int chunks = ctb::bn_chunks(C, (long long)B * L);
-  ctb::syncbn_bwd_stats_kernel<<<C, ctb::kBnThreads, 0, (cudaStream_t)stream>>>(x, grad_y, save_mean, save_invstd, grad_weight,
-                                                                               grad_bias, ex, B, L);
-  CTB_LAUNCH_CHECK();
-  ctb::syncbn_bwd_apply_kernel<<<dim3(C, chunks), ctb::kBnThreads, 0, (cudaStream_t)stream>>>(x, grad_y, weight, save_mean,
-                                                                                          save_invstd, grad_x, ex, B, L);
+  const long long per = (long long)B * L;
+  const dim3 gs(C, ctb::bn_chunks(C, per, ctb::kBnMaxChunks, 8192)), ga(C, ctb::bn_chunks(C, per, 65535, 4096));
+  cudaStream_t sm = (cudaStream_t)stream;
+  if (bn_vec4(L, {x, grad_y, grad_x})) {
+    ctb::syncbn_bwd_stats_kernel<4><<<gs, ctb::kBnThreads, 0, sm>>>(x, grad_y, save_mean, save_invstd, grad_weight, grad_bias,
+                                                                    ex, B, L);
+    ctb::syncbn_bwd_apply_kernel<4><<<ga, ctb::kBnThreads, 0, sm>>>(x, grad_y, weight, save_mean, save_invstd, grad_x, ex, B, L);
+  } else {
+    ctb::syncbn_bwd_stats_kernel<1><<<gs, ctb::kBnThreads, 0, sm>>>(x, grad_y, save_mean, save_invstd, grad_weight, grad_bias,
+                                                                    ex, B, L);
+    ctb::syncbn_bwd_apply_kernel<1><<<ga, ctb::kBnThreads, 0, sm>>>(x, grad_y, weight, save_mean, save_invstd, grad_x, ex, B, L);
+  }
   CTB_LAUNCH_CHECK();
   return CTB_OK;
 }

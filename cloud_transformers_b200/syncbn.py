@@ -53,11 +53,18 @@ class _ExchangePool:
                 table[i, 1, r] = peers[r] + f_off
         self.table = table.to(device)
         self.local = torch.zeros((len(blocks), 4), dtype=torch.int32, device=device)     # epoch [1] | done [2] | pad
+        lib = _lib.load()
+        s_offs, s_total = [], 0                    # chunk partials + chunk counters of the statistics kernels
+        for C in blocks:
+            s_offs.append(s_total)
+            s_total += (int(lib.ctb_syncbn_scratch_bytes(C)) + 15) // 16 * 16
+        self.scratch = torch.zeros(max(s_total, 16), dtype=torch.uint8, device=device)
         self.structs = []
         for i in range(len(blocks)):
             st = _lib.CtbBnExchange(
                 ctypes.c_void_p(self.table[i, 0].data_ptr()), ctypes.c_void_p(self.table[i, 1].data_ptr()),
-                ctypes.c_void_p(self.local[i].data_ptr()), ctypes.c_void_p(self.local[i].data_ptr() + 4), self.rank, W)
+                ctypes.c_void_p(self.local[i].data_ptr()), ctypes.c_void_p(self.local[i].data_ptr() + 4),
+                ctypes.c_void_p(self.scratch.data_ptr() + s_offs[i]), self.rank, W)
             self.structs.append(st)
 
 
@@ -76,7 +83,7 @@ class _SyncBNFn(torch.autograd.Function):
         ctx.save_for_backward(xc, weight, mean, invstd)
         ctx.ex_bwd = ex_bwd
         ctx.has_bias = bias is not None
-        return y.view_as(x)
+        return y                                   # (same shape as x; not a view: in-place ReLU may follow)
 
     @staticmethod
     @once_differentiable

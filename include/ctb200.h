@@ -207,16 +207,19 @@ int ctb_chamfer_bwd(const float* xyz1, const float* xyz2, const float* grad_dist
  *   exchange block of one layer and direction, on EVERY rank in peer-mapped (symmetric) memory, zero-initialised:
  *       data f32 [2][world][2*C] followed anywhere by flag u32 [2][world]
  *   peer_data / peer_flag: DEVICE arrays of `world` pointers to that block's data / flag part on each rank;
- *   epoch u32 [1], done u32 [2]: ordinary device memory of this rank, zero-initialised, owned by this layer + direction.
+ *   epoch u32 [1], done u32 [2], scratch (ctb_syncbn_scratch_bytes(C) bytes, 8-byte aligned): ordinary device memory of
+ *   this rank, zero-initialised, owned by this layer + direction.
  * Equal B and L on every rank.  x, y, grad_y, grad_x: f32 [B, C, L] contiguous. */
 typedef struct ctb_bn_exchange {
   void* const* peer_data;
   void* const* peer_flag;
   uint32_t* epoch;
   uint32_t* done;
+  void* scratch;
   int32_t rank;
   int32_t world;
 } ctb_bn_exchange;
+uint64_t ctb_syncbn_scratch_bytes(int C);
 /* training-mode forward: y, save_mean / save_invstd f32 [C] (for the backward), running statistics updated in place
  * (may be NULL) with momentum and the unbiased variance, like nn.SyncBatchNorm. */
 int ctb_syncbn_fwd(const float* x, const float* weight, const float* bias, float* y, float* save_mean, float* save_invstd,

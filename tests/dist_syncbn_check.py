@@ -32,12 +32,12 @@ class Net(nn.Module):
         self.b4 = nn.BatchNorm1d(33)
 
     def forward(self, x):
-        y = torch.relu(self.b1(self.c1(x)))
+        y = torch.relu_(self.b1(self.c1(x)))
         y = self.b2(self.c2(y))                                   # [B, 20, L]
         B, _, L = y.shape
         v = self.b3(y.reshape(B, 5, 2, 2, L)).reshape(B, 20, L)
         w = self.b2d(y.reshape(B, 4, 5, L)).reshape(B, 20, L)
-        z = self.b4(self.lin((v + w).mean(-1)))                  # BatchNorm1d on [B, C]
+        z = self.b4(self.lin((v + w).mean(-1)))       # BatchNorm1d on [B, C]
         return z, v
 
 
@@ -86,6 +86,22 @@ def main():
                 close(bf1[k], bf0[k], "step %d buffer %s" % (step, k), floor=1e-2)   # b3's running mean is ~0
             else:
                 assert torch.equal(bf1[k], bf0[k]), k
+    # a layer big enough for several statistics CTAs per channel (chunk partials folded by the last one), an odd L
+    for shape in ((8, 16, 64, 64), (8, 3, 7, 9, 11)):
+        big = nn.Sequential(nn.BatchNorm2d(shape[1]) if len(shape) == 4 else nn.BatchNorm3d(shape[1])).to(dev)
+        with torch.no_grad():
+            big[0].weight.uniform_(0.5, 1.5), big[0].bias.uniform_(-1, 1)
+        nets = (nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(big)), syncbn.convert_sync_batchnorm(copy.deepcopy(big)))
+        xb = torch.randn(*shape, device=dev, generator=g) * (1 + rank) + 3 * rank
+        gb = torch.randn(*shape, device=dev, generator=g)
+        res = []
+        for net in nets:
+            xi = xb.clone().requires_grad_(True)
+            yb = net(xi)
+            (yb * gb).sum().backward()
+            res.append((yb.detach(), xi.grad, net[0].weight.grad, net[0].bias.grad, net[0].running_var.clone()))
+        for a, b, what in zip(res[1], res[0], ("output", "input gradient", "grad weight", "grad bias", "running_var")):
+            close(a, b, "%s of %s" % (what, shape), rel=2e-5)
     # the layers replay inside a CUDA graph (device-side epochs, fixed pointers).  A fresh copy whose first backward
     # runs on the warm-up stream: gradient accumulators created on the legacy default stream cannot be captured
     ours = syncbn.convert_sync_batchnorm(copy.deepcopy(base))
