@@ -105,6 +105,7 @@ ent_scatter_kernel(const float* __restrict__ feat, const float* __restrict__ pad
   uint16_t* cs = (uint16_t*)(kind + G);                           // [CS]      first entry of every cell
 
   asm volatile("griddepcontrol.launch_dependents;");   // see tile_scatter_kernel
+  CTB_STAMP_INIT;
   const int f0 = (blockIdx.x % groups) * FG;
   const int unit = blockIdx.x / groups;
   const int fgn = min(FG, F - f0);
@@ -118,22 +119,20 @@ ent_scatter_kernel(const float* __restrict__ feat, const float* __restrict__ pad
     uint4* dst = reinterpret_cast<uint4*>(cs);
     for (int i = threadIdx.x; i < (CS >> 3); i += T) dst[i] = __ldg(src + i);
   }
-  for (int qq = 0; qq < LP; ++qq) {
-    const int fq = f0 + 4 * qq;
-    if (fq >= F) break;
-    const float* fp = fu + (size_t)(4 * qq) * N;
-#pragma unroll 2
-    for (int n = threadIdx.x; n < N; n += T) {
-      float v[4];
+  // (a lane takes (point, channel quad): the LP lanes of a point store its 16 LP bytes contiguously -- no bank
+  // conflicts -- and a warp's load of one channel plane covers full 32-byte sectors)
+#pragma unroll 4
+  for (int i = threadIdx.x; i < N * LP; i += T) {
+    const int n = i / LP, qq = i % LP;
+    float v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = (fq + k < F) ? __ldg(fp + (size_t)k * N + n) : 0.0f;
-      if (pu) {
-        const float pd = __ldg(pu + n);
+    for (int k = 0; k < 4; ++k) v[k] = (4 * qq + k < fgn) ? __ldg(fu + (size_t)(4 * qq + k) * N + n) : 0.0f;
+    if (pu) {
+      const float pd = __ldg(pu + n);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = CTB_FMUL(v[k], pd);
-      }
-      *reinterpret_cast<float4*>(xs + (size_t)n * FG + 4 * qq) = make_float4(v[0], v[1], v[2], v[3]);
+      for (int k = 0; k < 4; ++k) v[k] = CTB_FMUL(v[k], pd);
     }
+    *reinterpret_cast<float4*>(xs + (size_t)n * FG + 4 * qq) = make_float4(v[0], v[1], v[2], v[3]);
   }
 
   const int g = threadIdx.x / LP, q = threadIdx.x % LP;
@@ -143,6 +142,7 @@ ent_scatter_kernel(const float* __restrict__ feat, const float* __restrict__ pad
   // the output tile is channel-last [cell][FG]: a finished segment leaves with one 16-byte store per array
   const unsigned ov_q = smem_u32(ov) + (unsigned)q * 16u, ot_q = smem_u32(ot) + (unsigned)q * 16u;
   __syncthreads();
+  CTB_STAMP(10);
 
   int ca = 0;
   while (ca < C) {
@@ -158,68 +158,103 @@ ent_scatter_kernel(const float* __restrict__ feat, const float* __restrict__ pad
       if constexpr (!SUM) ot[i] = 0xffffffffu;
     }
     __syncthreads();
+    CTB_STAMP(11);
 
     // ---- windows ---------------------------------------------------------------------------------------
+    // The 8-byte records of a window are fetched ONCE, 16 bytes per lane: the LP lanes of a window load one aligned
+    // block of EB = 2 LP consecutive records (64 bytes at LP = 4) and hand them round by shuffle, the next block
+    // being in flight meanwhile.  (Per-record loads re-read a 128-byte line 16 times; with ~225 KB of shared memory
+    // carved out, the 28 KB that is left of L1 does not hold the 256 lines the windows of a CTA are walking.)
+    constexpr int EB = 2 * LP;
     const int L = (cnt + G - 1) / G;
     const int j0 = min(cnt, g * L), j1 = min(cnt, j0 + L);
+    const bool active = j0 < j1;
+    int cur = 0;
+    bool open_left = false;
+    if (active) {
+      cur = (int)(__ldg(&rec[j0].x) >> ebits);
+      open_left = j0 > 0 && (int)(__ldg(&rec[j0 - 1].x) >> ebits) == cur;
+    }
+    const int hcell = cur;
+    int my_kind = BIN_NONE;
     bool head_closing = false;
-    int hcell = 0, my_kind = BIN_NONE;
-    if (j0 < j1) {
-      int cur = (int)(__ldg(&rec[j0].x) >> ebits);
-      const bool open_left = j0 > 0 && (int)(__ldg(&rec[j0 - 1].x) >> ebits) == cur;
-      hcell = cur;
+    {
       unsigned rel = (unsigned)(cur - ca) * (FG * 4u);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       unsigned g0 = 0xffffffffu, g1 = 0xffffffffu, g2 = 0xffffffffu, g3 = 0xffffffffu;
-#pragma unroll 2
-      for (int j = j0; j < j1; ++j) {
-        float v0, v1, v2, v3;
-        const uint2 r = __ldg(rec + j);
-        const unsigned tg = r.x;
-        const float w = __uint_as_float(r.y);
-        const unsigned xa = xs_q + (tg & nmask) * (FG * 4u);
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "r"(xa));
-        const int c = (int)(tg >> ebits);
-        if (c != cur) {
-          // the segment is finished (a first segment that continues an earlier window is finished off after the
-          // barrier: its partial waits in the tile like any other result)
+      const int A0 = base + j0, A1 = base + j1;            // the window in record indices of the unit
+      const int NB = (L + 2 * EB - 2) / EB;                // blocks a window can touch (same for the whole CTA)
+      const uint4* e4 = reinterpret_cast<const uint4*>(eu);
+      int blk = A0 / EB;
+      auto fetch = [&](int bk) {
+        const int p = bk * LP + q;                          // record pair
+        return (active && bk * EB < A1 && 2 * p < E) ? __ldg(e4 + p) : make_uint4(0u, 0u, 0u, 0u);
+      };
+      uint4 rv = fetch(blk);
+      for (int t = 0; t < NB; ++t, ++blk) {
+        const uint4 rn = fetch(blk + 1);
+        const int ab = blk * EB;
+#pragma unroll
+        for (int k = 0; k < EB; ++k) {
+          unsigned tg = (k & 1) ? rv.z : rv.x, wb = (k & 1) ? rv.w : rv.y;
+          if constexpr (LP > 1) {
+            tg = __shfl_sync(0xffffffffu, tg, k >> 1, LP);
+            wb = __shfl_sync(0xffffffffu, wb, k >> 1, LP);
+          }
+          const int a = ab + k;
+          if (a >= A0 && a < A1) {
+            float v0, v1, v2, v3;
+            const float w = __uint_as_float(wb);
+            const unsigned xa = xs_q + (tg & nmask) * (FG * 4u);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "r"(xa));
+            const int c = (int)(tg >> ebits);
+            if (c != cur) {
+              // the segment is finished (a first segment that continues an earlier window is finished off after the
+              // barrier: its partial waits in the tile like any other result)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ov_q + rel), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+              if constexpr (!SUM)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ot_q + rel), "r"(g0), "r"(g1), "r"(g2), "r"(g3) : "memory");
+              cur = c;
+              rel = (unsigned)(c - ca) * (FG * 4u);
+              a0 = a1 = a2 = a3 = 0.0f;
+              g0 = g1 = g2 = g3 = 0xffffffffu;
+            }
+            const float t0 = CTB_FMUL(v0, w), t1 = CTB_FMUL(v1, w), t2 = CTB_FMUL(v2, w), t3 = CTB_FMUL(v3, w);
+            if constexpr (SUM) {
+              a0 = CTB_FADD(a0, t0);
+              a1 = CTB_FADD(a1, t1);
+              a2 = CTB_FADD(a2, t2);
+              a3 = CTB_FADD(a3, t3);
+            } else {
+              if (t0 > a0) { a0 = t0; g0 = tg; }
+              if (t1 > a1) { a1 = t1; g1 = tg; }
+              if (t2 > a2) { a2 = t2; g2 = tg; }
+              if (t3 > a3) { a3 = t3; g3 = tg; }
+            }
+          }
+        }
+        rv = rn;
+      }
+      if (active) {
+        const bool open_right = j1 < cnt && (int)(__ldg(&rec[j1].x) >> ebits) == cur;
+        const bool single = cur == hcell;                    // the window never left its first cell
+        if (open_right) {
+          // the cell goes on in the next window: park the partial (the closing window folds it in)
+          my_kind = (single && open_left) ? BIN_WHOLE : BIN_TAIL;
+          *reinterpret_cast<float4*>(pacc + (size_t)g * FG + 4 * q) = make_float4(a0, a1, a2, a3);
+          if constexpr (!SUM) *reinterpret_cast<uint4*>(ptag + (size_t)g * FG + 4 * q) = make_uint4(g0, g1, g2, g3);
+        } else {
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ov_q + rel), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
           if constexpr (!SUM)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ot_q + rel), "r"(g0), "r"(g1), "r"(g2), "r"(g3) : "memory");
-          cur = c;
-          rel = (unsigned)(c - ca) * (FG * 4u);
-          a0 = a1 = a2 = a3 = 0.0f;
-          g0 = g1 = g2 = g3 = 0xffffffffu;
         }
-        const float t0 = CTB_FMUL(v0, w), t1 = CTB_FMUL(v1, w), t2 = CTB_FMUL(v2, w), t3 = CTB_FMUL(v3, w);
-        if constexpr (SUM) {
-          a0 = CTB_FADD(a0, t0);
-          a1 = CTB_FADD(a1, t1);
-          a2 = CTB_FADD(a2, t2);
-          a3 = CTB_FADD(a3, t3);
-        } else {
-          if (t0 > a0) { a0 = t0; g0 = tg; }
-          if (t1 > a1) { a1 = t1; g1 = tg; }
-          if (t2 > a2) { a2 = t2; g2 = tg; }
-          if (t3 > a3) { a3 = t3; g3 = tg; }
-        }
+        head_closing = open_left && !(single && open_right);
       }
-      const bool open_right = j1 < cnt && (int)(__ldg(&rec[j1].x) >> ebits) == cur;
-      const bool single = cur == hcell;                    // the window never left its first cell
-      if (open_right) {
-        // the cell goes on in the next window: park the partial (the closing window folds it in)
-        my_kind = (single && open_left) ? BIN_WHOLE : BIN_TAIL;
-        *reinterpret_cast<float4*>(pacc + (size_t)g * FG + 4 * q) = make_float4(a0, a1, a2, a3);
-        if constexpr (!SUM) *reinterpret_cast<uint4*>(ptag + (size_t)g * FG + 4 * q) = make_uint4(g0, g1, g2, g3);
-      } else {
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ov_q + rel), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
-        if constexpr (!SUM)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ot_q + rel), "r"(g0), "r"(g1), "r"(g2), "r"(g3) : "memory");
-      }
-      head_closing = open_left && !(single && open_right);
     }
     if (q == 0) kind[g] = my_kind;
+    CTB_STAMP(15);
     __syncthreads();
+    CTB_STAMP(12);
     // ---- cells that span windows: the window that closes the cell folds the parked partials in window order,
     // then its own (already in the tile): ties keep the earliest entry, sums have a fixed order ----------------------
     if (head_closing) {
@@ -252,6 +287,7 @@ ent_scatter_kernel(const float* __restrict__ feat, const float* __restrict__ pad
       if constexpr (!SUM) *tt = rt;
     }
     __syncthreads();
+    CTB_STAMP(13);
     // ---- the tile leaves: a lane takes (cell, channel quad), a warp writes 32-byte runs of 4 planes -------------
     GT* zu = z + ((size_t)unit * F + f0) * C + ca;
     int* au = (!SUM && arg != nullptr) ? arg + ((size_t)unit * F + f0) * C + ca : nullptr;
@@ -277,6 +313,7 @@ ent_scatter_kernel(const float* __restrict__ feat, const float* __restrict__ pad
       }
     }
     __syncthreads();
+    CTB_STAMP(14);
     ca = cb;
   }
 }

@@ -16,7 +16,8 @@ from cloud_transformers_b200.hotpath import HotPath  # noqa: E402
 lib = _lib.load()
 fn = lib.ctb_debug_phase
 fn.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
-names = ["init", "compact", "prepass", "pt loads", "max pass", "arg pass", "to fence", "tma store", "pre-fence", "fence"]
+names = ["init", "compact", "prepass", "pt loads", "max pass", "arg pass", "to fence", "tma store", "pre-fence", "fence",
+         "E:staging", "E:tile init", "E:wait for slowest window", "E:fold", "E:write-out", "E:windows (thread 0)"]
 classes = sys.argv[1].split(",") if len(sys.argv) > 1 else ["a2d", "a3d"]
 dev = torch.device("cuda:0")
 gen = torch.Generator(device=dev).manual_seed(42)
@@ -30,9 +31,10 @@ for name, dim, W, F in bench.CLASSES:
     for op in ("splat_fwd", "slice_bwd"):
         fn(buf, 1)
         if op == "splat_fwd":
-            hp.splat_fwd(keys, feat)
+            hp.splat_fwd_only(keys, feat)
         else:
             hp.slice_bwd(keys, conv, go)
         fn(buf, 0)
-        tot = float(sum(buf[:10])) or 1.0
-        print(name, op, " ".join("%s=%.0f%%" % (n, 100.0 * buf[i] / tot) for i, n in enumerate(names)), "cycles/CTA-sum", int(tot))
+        tot = float(sum(buf[:16])) or 1.0
+        print(name, op, " ".join("%s=%.0f%%" % (n, 100.0 * buf[i] / tot) for i, n in enumerate(names) if buf[i]),
+              "cycles/CTA-sum", int(tot))
