@@ -62,7 +62,7 @@ SIGNATURES = {
     "ctb_plan_build": (_I, [_P, _P, ctypes.c_size_t, _SH, _P]),
     "ctb_splat_fwd_keys": (_I, [_P, _P, _P, _P, _P, _SH, _I, _I, _P, _P]),
     "ctb_splat_bwd_keys": (_I, [_P, _P, _P, _P, _P, _P, _P, _SH, _I, _I, _P]),
-    "ctb_slice_fwd_keys": (_I, [_P, _P, _P, _P, _SH, _I, _P]),
+    "ctb_slice_fwd_keys": (_I, [_P, _P, _P, _P, _SH, _I, _P, _P]),
     "ctb_slice_bwd_keys": (_I, [_P, _P, _P, _P, _P, _P, _SH, _I, _P, _P]),
     "ctb_project_fwd": (_I, [_P, _P, ctypes.c_float, _P, _P, _P, _P, _SH, _P]),
     "ctb_project_fwd_stats": (_I, [_P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _SH, _P]),

@@ -9,6 +9,7 @@
 #include "ctb_tile.cuh"
 #include "ctb_tile_cl.cuh"
 #include "ctb_binned.cuh"
+#include "ctb_sgather.cuh"
 #include "ctb_project.cuh"
 #include "ctb_chamfer.cuh"
 #include "ctb_syncbn.cuh"
@@ -359,9 +360,18 @@ int ctb_plan_used(const ctb_shape* shape, int mode) {
   return (mode == CTB_MODE_DETERMINISTIC ? binned_ok(shape) : binned_in_tile(shape, true)) ? 1 : 0;
 }
 
+// Slice forward in sorted point order (ctb_sgather.cuh) where the shape's plan exists anyway
+inline bool sorted_slice_ok(const ctb_shape* s, int mode) {
+  static const bool off = getenv("CTB_NO_SORTED_SLICE") != nullptr;
+  ctb::SortGatherConfig sc;
+  return !off && (mode == CTB_MODE_TILE || mode == CTB_MODE_DETERMINISTIC) && ctb_plan_used(s, mode) &&
+         ctb::sgather_config(s, &sc);
+}
+
 int ctb_op_uses_plan(const ctb_shape* shape, int op, int reduce, int mode) {
   if (check_shape(shape, true)) return 0;
-  if (op != CTB_OP_SPLAT_FWD && op != CTB_OP_SLICE_BWD) return 0;          // the gathers never read it
+  if (op == CTB_OP_SLICE_FWD) return sorted_slice_ok(shape, mode) ? 1 : 0;
+  if (op != CTB_OP_SPLAT_FWD && op != CTB_OP_SLICE_BWD) return 0;          // the backward gathers never read it
   const bool sum = op == CTB_OP_SLICE_BWD || reduce == CTB_REDUCE_SUM;
   if (mode == CTB_MODE_DETERMINISTIC) return binned_ok(shape) ? 1 : 0;
   if (mode == CTB_MODE_TILE) return binned_in_tile(shape, sum) ? 1 : 0;
@@ -443,11 +453,14 @@ int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pa
 }
 
 int ctb_slice_fwd_keys(const float* keys, const void* grid_any, const float* pad, float* out,
-                       const ctb_shape* shape, int mode, void* stream) {
+                       const ctb_shape* shape, int mode, const void* plan, void* stream) {
   const float* grid = (const float*)grid_any;
   int st = check_shape(shape, true);
   if (st) return st;
   if (!keys || !grid || !out) return CTB_ERR_INVALID_ARGUMENT;
+  if (plan && sorted_slice_ok(shape, mode) && (((uintptr_t)grid | (uintptr_t)out) & 15u) == 0)
+    return cuda_status(shape->dim == 2 ? ctb::sorted_slice_fwd<2>(keys, grid, pad, out, plan, shape, (cudaStream_t)stream)
+                                       : ctb::sorted_slice_fwd<3>(keys, grid, pad, out, plan, shape, (cudaStream_t)stream));
   if (mode == CTB_MODE_DETERMINISTIC || mode == CTB_MODE_TILE)
     return cuda_status(gather_dispatch<ctb::GATHER_SLICE_FWD>(keys, grid_any, nullptr, nullptr, pad, out, nullptr, shape,
                                                                (cudaStream_t)stream));

@@ -365,9 +365,18 @@ class _FusedSliceFn(torch.autograd.Function):
         gd = _grid_dtype_code(grid.dtype, mode)
         g_c = _grid_c(grid, gd)
         out = torch.empty((B, geom.heads * F, N), dtype=torch.float32, device=g_c.device)
+        sh = geom.shape(B, F, N, gd)
+        # the sorted-order gather reads the plan where the block has one anyway: already built (Splat forward on the
+        # coarse grids), being built on the side stream, or due in this op's backward
+        plan = None
+        if (mode != _lib.MODE_ATOMIC and config.use_plan
+                and _lib.load().ctb_op_uses_plan(ctypes.byref(sh), _lib.OP_SLICE_FWD, 0, mode)
+                and (handle._plan is not None
+                     or (torch.is_grad_enabled() and (grid.requires_grad or keys.requires_grad)))):
+            plan = handle.plan()
         with torch.cuda.device(g_c.device):
-            _call("ctb_slice_fwd_keys", _ptr(k), _ptr(g_c), _ptr(p_c), _ptr(out), ctypes.byref(geom.shape(B, F, N, gd)),
-                  mode, _stream(g_c))
+            _call("ctb_slice_fwd_keys", _ptr(k), _ptr(g_c), _ptr(p_c), _ptr(out), ctypes.byref(sh), mode, _ptr(plan),
+                  _stream(g_c))
         ctx.save_for_backward(k, g_c, p_c)
         ctx.handle = handle
         ctx.grid_dtype = grid.dtype

@@ -56,6 +56,8 @@ class HotPath:
         # is built on a side stream under the two forward passes instead of in front of them.
         self.plan_in_fwd = self.plan is not None and bool(lib.ctb_op_uses_plan(
             self._sh, _lib.OP_SPLAT_FWD, self.reduce, self.modes[_lib.OP_SPLAT_FWD]))
+        self.slice_fwd_uses_plan = self.plan is not None and bool(lib.ctb_op_uses_plan(
+            self._sh, _lib.OP_SLICE_FWD, self.reduce, self.modes[_lib.OP_SLICE_FWD]))
         self._side = None
 
     # number of kernel launches (ours) per full fwd+bwd pass, for bench.py's gpu_launches claim
@@ -89,7 +91,7 @@ class HotPath:
 
     def slice_fwd(self, keys, grid, pad=None):
         self._call("ctb_slice_fwd_keys", _ptr(keys), _ptr(grid), _ptr(pad), _ptr(self.out), self._sh,
-              self.modes[_lib.OP_SLICE_FWD], _stream(keys))
+              self.modes[_lib.OP_SLICE_FWD], _ptr(self.plan) if self.slice_fwd_uses_plan else None, _stream(keys))
         return self.out
 
     def slice_bwd(self, keys, grid, grad_out, pad=None):
@@ -114,8 +116,11 @@ class HotPath:
             with torch.cuda.stream(self._side):
                 self.build_plan(keys)
             self.splat_fwd_only(keys, feat, pad)
+            if self.slice_fwd_uses_plan:
+                cur.wait_stream(self._side)
             self.slice_fwd(keys, conv, pad)
-            cur.wait_stream(self._side)
+            if not self.slice_fwd_uses_plan:
+                cur.wait_stream(self._side)
         else:
             self.splat_fwd(keys, feat, pad)
             self.slice_fwd(keys, conv, pad)

@@ -135,7 +135,7 @@ int ctb_mode_supported(const ctb_shape* shape, int op, int reduce, int mode);
  * ctb_plan_used: 1 if the kernels of `mode` use a plan on this shape (then the caller should build one and pass it;
  * DETERMINISTIC requires it, TILE falls back to its shared-memory tile scatters when plan == NULL). */
 int ctb_plan_used(const ctb_shape* shape, int mode);
-/* 1 if `op` (CTB_OP_SPLAT_FWD with `reduce`, or CTB_OP_SLICE_BWD) reads the plan in `mode` on this shape.  Lets a
+/* 1 if `op` (CTB_OP_SPLAT_FWD with `reduce`, CTB_OP_SLICE_FWD, or CTB_OP_SLICE_BWD) reads the plan in `mode` on this shape.  Lets a
  * caller build the plan off the critical path when only the backward needs it (16^3 x F16: the forward max keeps the
  * tile scatter, the grad_grid sum of Slice backward is plan-based). */
 int ctb_op_uses_plan(const ctb_shape* shape, int op, int reduce, int mode);
@@ -149,8 +149,10 @@ int ctb_splat_fwd_keys(const float* keys, const float* features, const float* pa
 int ctb_splat_bwd_keys(const float* keys, const float* features, const float* pad, const void* grad_z,
                        const int32_t* arg, float* grad_features, float* grad_keys, const ctb_shape* shape,
                        int reduce, int mode, void* stream);
+/* plan: may be NULL; where ctb_op_uses_plan(shape, CTB_OP_SLICE_FWD, ..) is 1, a plan lets the gather walk the points
+ * in cell-sorted order (same results bit for bit, fewer shared-memory bank conflicts). */
 int ctb_slice_fwd_keys(const float* keys, const void* grid, const float* pad, float* out,
-                       const ctb_shape* shape, int mode, void* stream);
+                       const ctb_shape* shape, int mode, const void* plan, void* stream);
 int ctb_slice_bwd_keys(const float* keys, const void* grid, const float* pad, const float* grad_out,
                        void* grad_grid, float* grad_keys, const ctb_shape* shape, int mode,
                        const void* plan, void* stream);

@@ -34,7 +34,7 @@ def test_argument_validation_without_gpu():
     sh = _lib.make_shape(2, 4, 4, 128, 2, (16, 16))
     # NULL pointers are rejected before any CUDA call
     assert lib.ctb_positions_fwd(None, None, None, ctypes.byref(sh), None) == _lib.CTB_ERR_INVALID_ARGUMENT
-    assert lib.ctb_slice_fwd_keys(None, None, None, None, ctypes.byref(sh), 0, None) == _lib.CTB_ERR_INVALID_ARGUMENT
+    assert lib.ctb_slice_fwd_keys(None, None, None, None, ctypes.byref(sh), 0, None, None) == _lib.CTB_ERR_INVALID_ARGUMENT
     bad = _lib.make_shape(2, 4, 4, 128, 4, (16, 16))
     assert lib.ctb_positions_fwd(None, None, None, ctypes.byref(bad), None) == _lib.CTB_ERR_INVALID_ARGUMENT
     tiny = _lib.make_shape(2, 4, 4, 128, 2, (1, 16))

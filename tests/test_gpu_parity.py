@@ -5,6 +5,8 @@ full sizes -- through size-independent properties.
 Tolerances (north star): cell indices, corner weights and the Splat-max grid are BIT-EXACT; everything
 that sums floats is within rel 1e-5 (absolute floor 1e-5 * max|ref|).
 """
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -375,6 +377,33 @@ def test_tile_sum_is_order_independent_and_accurate():
         err = np.abs(outs[0].astype(np.float64) - ex)
         bound = 2.0 ** -24 * np.abs(ex) + N * 2.0 ** -39 * float(np.abs(feat).max())
         assert (err <= bound).all(), float((err - bound).max())
+
+
+def test_sorted_slice_forward_is_bit_identical_to_the_tile_gather_and_matches_the_oracle():
+    """Dense grids: with a plan, Slice forward walks the points in cell-sorted order (ctb_sgather.cuh) -- same
+    arithmetic per (point, channel), so the same bits as the index-order tile gather; layers/cloud_transform.py:204-211."""
+    lib = _lib.load()
+    for dim, W, H, F, N, B, pad_on in [(3, 8, 2, 32, 2048, 2, False), (2, 16, 2, 16, 2048, 1, True), (3, 16, 2, 16, 2048, 1, True),
+                                        (3, 8, 2, 12, 1000, 1, True), (2, 16, 3, 5, 300, 2, False)]:
+        keys, feat, pad = make_inputs(17, B, H, dim, F, N, pad=pad_on, dist="onecell" if N == 300 else "tanh")
+        sizes = O._sizes(W, dim)
+        geom = CF.Geometry(sizes, H, dim)
+        rng = np.random.default_rng(5)
+        conv = rng.standard_normal((B, H * F) + tuple(sizes)).astype(np.float32)
+        sh = geom.shape(B, F, N, _lib.DTYPE_F32)
+        assert lib.ctb_op_uses_plan(ctypes.byref(sh), _lib.OP_SLICE_FWD, 0, _lib.MODE_TILE) == 1, (dim, W, F, N)
+        outs = []
+        for use_plan in (True, False):
+            ctb.config.mode = "tile"
+            ctb.config.use_plan = use_plan
+            h = CF.PositionsHandle(t(keys), geom)
+            with torch.no_grad():
+                if use_plan:
+                    h.plan()                      # as after a plan-based Splat forward
+                outs.append(n(CF.fused_slice(h, t(conv), t(pad))))
+        assert np.array_equal(outs[0], outs[1])
+        lc, idx = O.positions_fwd(keys, W, H, dim)
+        assert_close(outs[0], O.slice_fwd(lc, idx, conv, H, pad), "sorted slice fwd %s" % ((dim, W, F, N),))
 
 
 def test_tile_sum_limb_headroom_worst_case():
