@@ -12,6 +12,7 @@
 #include "ctb_sgather.cuh"
 #include "ctb_project.cuh"
 #include "ctb_chamfer.cuh"
+#include "ctb_emd.cuh"
 #include "ctb_syncbn.cuh"
 
 namespace {
@@ -582,6 +583,21 @@ int ctb_chamfer_bwd(const float* xyz1, const float* xyz2, const float* grad_dist
   if (B > 65535) return CTB_ERR_UNSUPPORTED;
   return cuda_status(ctb::chamfer_backward(xyz1, xyz2, grad_dist1, grad_dist2, idx1, idx2, grad_xyz1, grad_xyz2, B, n, m,
                                            (cudaStream_t)stream));
+}
+
+int ctb_emd_max_points(void) { return ctb::kEmdMaxPoints; }
+
+int ctb_emd_fwd(const float* xyz1, const float* xyz2, float* dist, int32_t* assignment, int B, int n, float eps, int iters,
+                void* stream) {
+  if (!xyz1 || !xyz2 || !dist || !assignment || B <= 0 || n <= 0 || iters <= 0) return CTB_ERR_INVALID_ARGUMENT;
+  if (n > ctb::kEmdMaxPoints) return CTB_ERR_UNSUPPORTED;
+  return cuda_status(ctb::emd_forward(xyz1, xyz2, dist, assignment, B, n, eps, iters, (cudaStream_t)stream));
+}
+
+int ctb_emd_bwd(const float* xyz1, const float* xyz2, const float* grad_dist, const int32_t* assignment, float* grad_xyz1,
+                int B, int n, void* stream) {
+  if (!xyz1 || !xyz2 || !grad_dist || !assignment || !grad_xyz1 || B <= 0 || n <= 0) return CTB_ERR_INVALID_ARGUMENT;
+  return cuda_status(ctb::emd_backward(xyz1, xyz2, grad_dist, assignment, grad_xyz1, B, n, (cudaStream_t)stream));
 }
 
 static int bn_exchange_of(const ctb_bn_exchange* ex, int C, ctb::BnExchange* out) {

@@ -201,6 +201,19 @@ int ctb_chamfer_bwd(const float* xyz1, const float* xyz2, const float* grad_dist
                     void* stream);
 
 /* ---- N2: SyncBatchNorm with the cross-GPU exchange fused into its kernels (train_classification.py:107-109) -------- */
+/* Replaces emd_linear/emd_cuda.cu:223-275 emd_cuda_forward as bound by emd_linear/emd_module.py:30-63: the auction
+ * approximation of the Earth Mover's Distance between two clouds of n points each, xyz f32 [B, n, 3] in [0, 1]^3.
+ * dist f32 [B, n] = squared distance of every point of xyz1 to its assigned point of xyz2, assignment i32 [B, n]
+ * (not guaranteed to be a bijection: sources still unassigned in the last iteration take the target they bid on).
+ * One launch for all `iters` iterations; no scratch tensors (the reference's eleven work tensors live in shared
+ * memory).  n <= ctb_emd_max_points() (8192), any n (the reference needs multiples of 1024), any B. */
+int ctb_emd_max_points(void);
+int ctb_emd_fwd(const float* xyz1, const float* xyz2, float* dist, int32_t* assignment, int B, int n, float eps, int iters,
+                void* stream);
+/* Replaces emd_cuda_backward (emd_cuda.cu:277-316): grad_xyz1 f32 [B, n, 3], fully written; xyz2 gets no gradient. */
+int ctb_emd_bwd(const float* xyz1, const float* xyz2, const float* grad_dist, const int32_t* assignment, float* grad_xyz1,
+                int B, int n, void* stream);
+
 /* Replaces torch.nn.SyncBatchNorm's statistics kernel -> NCCL all_gather / all_reduce -> combine -> elementwise chain
  * (106 layers = 212 small collectives per step in model_zoo/scanobject/classifier.py) by two kernels per direction whose
  * exchange is a one-shot all-gather over NVLink peer memory: the statistics kernel stores its per-channel partial sums
