@@ -72,7 +72,8 @@ SIGNATURES = {
     "ctb_chamfer_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _I, _I, _I, _P]),
     "ctb_chamfer_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "ctb_emd_max_points": (_I, []),
-    "ctb_emd_fwd": (_I, [_P, _P, _P, _P, _I, _I, ctypes.c_float, _I, _P]),
+    "ctb_emd_workspace_bytes": (ctypes.c_size_t, [_I, _I]),
+    "ctb_emd_fwd": (_I, [_P, _P, _P, _P, _P, ctypes.c_size_t, _I, _I, ctypes.c_float, _I, _P]),
     "ctb_emd_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "ctb_syncbn_scratch_bytes": (ctypes.c_uint64, [_I]),
     "ctb_syncbn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(CtbBnExchange), _I, _I, _I, ctypes.c_float,

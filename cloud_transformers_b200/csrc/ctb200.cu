@@ -587,11 +587,17 @@ int ctb_chamfer_bwd(const float* xyz1, const float* xyz2, const float* grad_dist
 
 int ctb_emd_max_points(void) { return ctb::kEmdMaxPoints; }
 
-int ctb_emd_fwd(const float* xyz1, const float* xyz2, float* dist, int32_t* assignment, int B, int n, float eps, int iters,
-                void* stream) {
+size_t ctb_emd_workspace_bytes(int B, int n) {
+  return (B > 0 && n > 0 && n <= ctb::kEmdMaxPoints) ? ctb::emd_workspace_bytes(B, n) : 0;
+}
+
+int ctb_emd_fwd(const float* xyz1, const float* xyz2, float* dist, int32_t* assignment, void* workspace,
+                size_t workspace_bytes, int B, int n, float eps, int iters, void* stream) {
   if (!xyz1 || !xyz2 || !dist || !assignment || B <= 0 || n <= 0 || iters <= 0) return CTB_ERR_INVALID_ARGUMENT;
   if (n > ctb::kEmdMaxPoints) return CTB_ERR_UNSUPPORTED;
-  return cuda_status(ctb::emd_forward(xyz1, xyz2, dist, assignment, B, n, eps, iters, (cudaStream_t)stream));
+  const size_t need = ctb::emd_workspace_bytes(B, n);
+  if (need && (!workspace || workspace_bytes < need)) return CTB_ERR_WORKSPACE;
+  return cuda_status(ctb::emd_forward(xyz1, xyz2, dist, assignment, workspace, B, n, eps, iters, (cudaStream_t)stream));
 }
 
 int ctb_emd_bwd(const float* xyz1, const float* xyz2, const float* grad_dist, const int32_t* assignment, float* grad_xyz1,

@@ -3,7 +3,7 @@
 Same names and call: emdFunction.apply(xyz1, xyz2, eps, iters) -> (dist [B, n], assignment [B, n] int32), emdModule
 (emd_module.py:30-87; train_inpainter.py:187-189 takes torch.sqrt(dist).mean(1).mean()).  Gradient for xyz1 only, like
 the reference.  One kernel launch runs all iterations (csrc/ctb_emd.cuh); none of the reference's eleven scratch
-tensors is allocated.  GPU tensors only; any n <= 8192 (the reference: multiples of 1024), any batch size."""
+tensors is allocated up to 4096 points (above, one workspace).  GPU tensors only; any n <= 32768 (the reference: multiples of 1024), any batch size."""
 import ctypes
 
 import torch
@@ -29,9 +29,11 @@ class emdFunction(Function):
         xyz2 = xyz2.contiguous().float()
         dist = torch.empty(batchsize, n, device=xyz1.device)
         assignment = torch.empty(batchsize, n, device=xyz1.device, dtype=torch.int32)
+        nbytes = _lib.load().ctb_emd_workspace_bytes(batchsize, n)          # 0 up to 4096 points
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz1.device) if nbytes else None
         with torch.cuda.device(xyz1.device):
-            _call("ctb_emd_fwd", _ptr(xyz1), _ptr(xyz2), _ptr(dist), _ptr(assignment), batchsize, n, ctypes.c_float(eps),
-                  int(iters), _stream(xyz1))
+            _call("ctb_emd_fwd", _ptr(xyz1), _ptr(xyz2), _ptr(dist), _ptr(assignment), _ptr(ws), ctypes.c_size_t(nbytes),
+                  batchsize, n, ctypes.c_float(eps), int(iters), _stream(xyz1))
         ctx.save_for_backward(xyz1, xyz2, assignment)
         ctx.mark_non_differentiable(assignment)
         return dist, assignment

@@ -205,11 +205,14 @@ int ctb_chamfer_bwd(const float* xyz1, const float* xyz2, const float* grad_dist
  * approximation of the Earth Mover's Distance between two clouds of n points each, xyz f32 [B, n, 3] in [0, 1]^3.
  * dist f32 [B, n] = squared distance of every point of xyz1 to its assigned point of xyz2, assignment i32 [B, n]
  * (not guaranteed to be a bijection: sources still unassigned in the last iteration take the target they bid on).
- * One launch for all `iters` iterations; no scratch tensors (the reference's eleven work tensors live in shared
- * memory).  n <= ctb_emd_max_points() (8192), any n (the reference needs multiples of 1024), any B. */
+ * One launch for all `iters` iterations.  Up to 4096 points the reference's eleven work tensors live in shared memory
+ * (ctb_emd_workspace_bytes = 0, workspace may be NULL); larger clouds (the inpainting decoder: 16384) need
+ * ctb_emd_workspace_bytes(B, n) bytes of device scratch, uninitialised.  n <= ctb_emd_max_points() (32768), any n (the
+ * reference needs multiples of 1024), any B. */
 int ctb_emd_max_points(void);
-int ctb_emd_fwd(const float* xyz1, const float* xyz2, float* dist, int32_t* assignment, int B, int n, float eps, int iters,
-                void* stream);
+size_t ctb_emd_workspace_bytes(int B, int n);
+int ctb_emd_fwd(const float* xyz1, const float* xyz2, float* dist, int32_t* assignment, void* workspace,
+                size_t workspace_bytes, int B, int n, float eps, int iters, void* stream);
 /* Replaces emd_cuda_backward (emd_cuda.cu:277-316): grad_xyz1 f32 [B, n, 3], fully written; xyz2 gets no gradient. */
 int ctb_emd_bwd(const float* xyz1, const float* xyz2, const float* grad_dist, const int32_t* assignment, float* grad_xyz1,
                 int B, int n, void* stream);

@@ -30,15 +30,20 @@ def emd_auction(xyz1, xyz2, eps, iters):
         una = np.nonzero(asg == -1)[0]
         if una.size == 0:
             break
-        d = x2[None, :, :] - x1[una, None, :]                          # [U, n, 3]
-        sq = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
-        val = (3.0 - np.sqrt(sq).astype(np.float64) - price[None, :].astype(np.float64)).astype(F32)
-        best_i = val.argmax(axis=1)                                    # first maximum
-        rows = np.arange(una.size)
-        best = val[rows, best_i]
-        rest = val.copy()
-        rest[rows, best_i] = -np.inf
-        better = np.maximum(rest.max(axis=1), F32(-1e9)) if n > 1 else np.full(una.size, F32(-1e9))
+        best_i = np.empty(una.size, dtype=np.int64)
+        best = np.empty(una.size, dtype=F32)
+        better = np.empty(una.size, dtype=F32)
+        for c0 in range(0, una.size, 512):                             # (blocks of sources: memory)
+            u = una[c0:c0 + 512]
+            d = x2[None, :, :] - x1[u, None, :]                        # [u, n, 3]
+            sq = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+            val = (3.0 - np.sqrt(sq).astype(np.float64) - price[None, :].astype(np.float64)).astype(F32)
+            bi = val.argmax(axis=1)                                    # first maximum
+            rows = np.arange(u.size)
+            best_i[c0:c0 + 512] = bi
+            best[c0:c0 + 512] = val[rows, bi]
+            val[rows, bi] = -np.inf
+            better[c0:c0 + 512] = np.maximum(val.max(axis=1), F32(-1e9)) if n > 1 else F32(-1e9)
         inc = ((best - better).astype(F32) + eps).astype(F32)
         if last:
             asg[una] = best_i

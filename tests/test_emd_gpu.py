@@ -25,7 +25,8 @@ def clouds(seed, B, n, clustered=False):
 
 @pytest.mark.parametrize("B,n,eps,iters,clustered", [
     (2, 1024, 0.005, 50, False), (1, 2048, 0.005, 50, True), (3, 300, 0.01, 7, False), (1, 1000, 0.004, 400, True),
-    (2, 64, 0.005, 1, False), (1, 37, 1e-4, 3000, False), (1, 4096, 0.005, 20, True)])
+    (2, 64, 0.005, 1, False), (1, 37, 1e-4, 3000, False), (1, 4096, 0.005, 20, True),
+    (2, 9000, 0.005, 12, True)])      # above 4096 points: the state moves from shared memory to the global workspace
 def test_auction_matches_the_oracle_bit_for_bit(B, n, eps, iters, clustered):
     from cloud_transformers_b200.emd import emdModule
     a, b = clouds(n + iters, B, n, clustered)
@@ -57,12 +58,16 @@ def test_limits_and_errors():
     from cloud_transformers_b200 import _lib
     from cloud_transformers_b200.emd import emdModule
     lib = _lib.load()
-    assert lib.ctb_emd_max_points() == 8192
-    a = torch.rand(1, 8192, 3, device=DEV)
-    dist, asg = emdModule()(a, a.flip(1).contiguous(), 0.005, 30)
-    assert int(asg.min()) >= 0 and int(asg.max()) < 8192
+    assert lib.ctb_emd_max_points() == 32768
+    assert lib.ctb_emd_workspace_bytes(4, 4096) == 0 and lib.ctb_emd_workspace_bytes(4, 16384) >= 4 * 28 * 16384
+    for n in (4096, 8192, 16384):               # the largest shared-memory cloud; a workspace cloud; the inpainting decoder's size
+        a = torch.rand(2, n, 3, device=DEV)
+        dist, asg = emdModule()(a, a.flip(1).contiguous(), 0.005, 50)
+        assert int(asg.min()) >= 0 and int(asg.max()) < n
+        assert (asg == torch.arange(n - 1, -1, -1, device=DEV, dtype=torch.int32)).all()      # the clouds are permutations
+        assert float(dist.max()) == 0.0
     with pytest.raises(_lib.CtbError):
-        emdModule()(torch.rand(1, 8200, 3, device=DEV), torch.rand(1, 8200, 3, device=DEV), 0.005, 5)
+        emdModule()(torch.rand(1, 33000, 3, device=DEV), torch.rand(1, 33000, 3, device=DEV), 0.005, 5)
     with pytest.raises(Exception):
         emdModule()(torch.rand(1, 16, 3), torch.rand(1, 16, 3), 0.005, 5)          # CPU tensors: no fallback
 

@@ -44,7 +44,7 @@ def test_emd_against_the_reference_kernels():
     from cloud_transformers_b200.emd import emdModule
     mod = _ref("ref_emd")
     g = torch.Generator(device=DEV).manual_seed(1)
-    for B, n, eps, iters in [(4, 1024, 0.005, 50), (2, 2048, 0.005, 50), (2, 2048, 0.004, 3000)]:
+    for B, n, eps, iters in [(4, 1024, 0.005, 50), (2, 2048, 0.005, 50), (2, 2048, 0.004, 3000), (2, 16384, 0.005, 50)]:
         a = torch.rand(B, n, 3, device=DEV, generator=g)
         b = (a[:, torch.randperm(n, device=DEV, generator=g)] + 0.02 * torch.randn(B, n, 3, device=DEV, generator=g)).clamp(0, 1)
         d_ref, a_ref = ref_emd_forward(mod, a, b.contiguous(), eps, iters)

@@ -32,7 +32,7 @@ def timeit(fn, reps):
 g = torch.Generator(device=DEV).manual_seed(0)
 ref_emd, ref_ch = R.load("ref_emd"), R.load("ref_chamfer")
 print("EMD: B x n, eps, iters | ours ms | reference kernels ms | loss ours / reference")
-for B, n, eps, iters, reps in [(32, 2048, 0.005, 50, 10), (8, 2048, 0.005, 50, 10), (32, 2048, 0.004, 3000, 2), (8, 8192, 0.005, 50, 3)]:
+for B, n, eps, iters, reps in [(32, 2048, 0.005, 50, 10), (8, 2048, 0.005, 50, 10), (32, 2048, 0.004, 3000, 2), (8, 8192, 0.005, 50, 3), (2, 16384, 0.005, 50, 3), (2, 16384, 0.004, 3000, 1)]:
     a = torch.rand(B, n, 3, device=DEV, generator=g)
     b = (a[:, torch.randperm(n, device=DEV, generator=g)] + 0.02 * torch.randn(B, n, 3, device=DEV, generator=g)).clamp(0, 1).contiguous()
     t = timeit(lambda: emdModule()(a, b, eps, iters), reps)
