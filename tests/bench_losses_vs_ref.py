@@ -1,5 +1,6 @@
 """Completion-loss kernels (row N3): this library against the reference's own CUDA kernels (oracle/_ref/cuda_ext, test
-infrastructure) at the shapes the training scripts use.  python tools/bench_losses.py"""
+infrastructure -- which is why this script lives under tests/) at the shapes the training scripts use.
+    python tests/bench_losses_vs_ref.py          # not collected by pytest"""
 import os
 import sys
 
@@ -10,8 +11,7 @@ sys.path.insert(0, ROOT)
 from cloud_transformers_b200.chamfer import ChamferFunction  # noqa: E402
 from cloud_transformers_b200.emd import emdModule  # noqa: E402
 from oracle import build_ref_cuda as R  # noqa: E402
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-from test_losses_ref_gpu import ref_emd_forward  # noqa: E402
+from tests.test_losses_ref_gpu import ref_emd_forward  # noqa: E402
 
 DEV = "cuda:0"
 
