@@ -182,58 +182,69 @@ ent_scatter_kernel(const float* __restrict__ feat, const float* __restrict__ pad
       unsigned rel = (unsigned)(cur - ca) * (FG * 4u);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       unsigned g0 = 0xffffffffu, g1 = 0xffffffffu, g2 = 0xffffffffu, g3 = 0xffffffffu;
-      const int A0 = base + j0, A1 = base + j1;            // the window in record indices of the unit
-      const int NB = (L + 2 * EB - 2) / EB;                // blocks a window can touch (same for the whole CTA)
-      const uint4* e4 = reinterpret_cast<const uint4*>(eu);
-      int blk = A0 / EB;
-      auto fetch = [&](int bk) {
-        const int p = bk * LP + q;                          // record pair
-        return (active && bk * EB < A1 && 2 * p < E) ? __ldg(e4 + p) : make_uint4(0u, 0u, 0u, 0u);
-      };
-      uint4 rv = fetch(blk);
-      for (int t = 0; t < NB; ++t, ++blk) {
-        const uint4 rn = fetch(blk + 1);
-        const int ab = blk * EB;
-#pragma unroll
-        for (int k = 0; k < EB; ++k) {
-          unsigned tg = (k & 1) ? rv.z : rv.x, wb = (k & 1) ? rv.w : rv.y;
-          if constexpr (LP > 1) {
-            tg = __shfl_sync(0xffffffffu, tg, k >> 1, LP);
-            wb = __shfl_sync(0xffffffffu, wb, k >> 1, LP);
-          }
-          const int a = ab + k;
-          if (a >= A0 && a < A1) {
-            float v0, v1, v2, v3;
-            const float w = __uint_as_float(wb);
-            const unsigned xa = xs_q + (tg & nmask) * (FG * 4u);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "r"(xa));
-            const int c = (int)(tg >> ebits);
-            if (c != cur) {
-              // the segment is finished (a first segment that continues an earlier window is finished off after the
-              // barrier: its partial waits in the tile like any other result)
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ov_q + rel), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
-              if constexpr (!SUM)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ot_q + rel), "r"(g0), "r"(g1), "r"(g2), "r"(g3) : "memory");
-              cur = c;
-              rel = (unsigned)(c - ca) * (FG * 4u);
-              a0 = a1 = a2 = a3 = 0.0f;
-              g0 = g1 = g2 = g3 = 0xffffffffu;
-            }
-            const float t0 = CTB_FMUL(v0, w), t1 = CTB_FMUL(v1, w), t2 = CTB_FMUL(v2, w), t3 = CTB_FMUL(v3, w);
-            if constexpr (SUM) {
-              a0 = CTB_FADD(a0, t0);
-              a1 = CTB_FADD(a1, t1);
-              a2 = CTB_FADD(a2, t2);
-              a3 = CTB_FADD(a3, t3);
-            } else {
-              if (t0 > a0) { a0 = t0; g0 = tg; }
-              if (t1 > a1) { a1 = t1; g1 = tg; }
-              if (t2 > a2) { a2 = t2; g2 = tg; }
-              if (t3 > a3) { a3 = t3; g3 = tg; }
-            }
-          }
+      // one record of the window
+      auto take = [&](unsigned tg, unsigned wb) {
+        float v0, v1, v2, v3;
+        const float w = __uint_as_float(wb);
+        const unsigned xa = xs_q + (tg & nmask) * (FG * 4u);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "r"(xa));
+        const int c = (int)(tg >> ebits);
+        if (c != cur) {
+          // the segment is finished (a first segment that continues an earlier window is finished off after the
+          // barrier: its partial waits in the tile like any other result)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ov_q + rel), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+          if constexpr (!SUM)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ot_q + rel), "r"(g0), "r"(g1), "r"(g2), "r"(g3) : "memory");
+          cur = c;
+          rel = (unsigned)(c - ca) * (FG * 4u);
+          a0 = a1 = a2 = a3 = 0.0f;
+          g0 = g1 = g2 = g3 = 0xffffffffu;
         }
-        rv = rn;
+        const float t0 = CTB_FMUL(v0, w), t1 = CTB_FMUL(v1, w), t2 = CTB_FMUL(v2, w), t3 = CTB_FMUL(v3, w);
+        if constexpr (SUM) {
+          a0 = CTB_FADD(a0, t0);
+          a1 = CTB_FADD(a1, t1);
+          a2 = CTB_FADD(a2, t2);
+          a3 = CTB_FADD(a3, t3);
+        } else {
+          if (t0 > a0) { a0 = t0; g0 = tg; }
+          if (t1 > a1) { a1 = t1; g1 = tg; }
+          if (t2 > a2) { a2 = t2; g2 = tg; }
+          if (t3 > a3) { a3 = t3; g3 = tg; }
+        }
+      };
+      if (L < 2 * EB) {
+        // short windows (fine grids cut into many tiles): block fetches would mostly load records of the neighbours
+#pragma unroll 2
+        for (int j = j0; j < j1; ++j) {
+          const uint2 r = __ldg(rec + j);
+          take(r.x, r.y);
+        }
+      } else {
+        const int A0 = base + j0, A1 = base + j1;            // the window in record indices of the unit
+        const int NB = (L + 2 * EB - 2) / EB;                // blocks a window can touch (same for the whole CTA)
+        const uint4* e4 = reinterpret_cast<const uint4*>(eu);
+        int blk = A0 / EB;
+        auto fetch = [&](int bk) {
+          const int p = bk * LP + q;                          // record pair
+          return (active && bk * EB < A1 && 2 * p < E) ? __ldg(e4 + p) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        uint4 rv = fetch(blk);
+        for (int t = 0; t < NB; ++t, ++blk) {
+          const uint4 rn = fetch(blk + 1);
+          const int ab = blk * EB;
+#pragma unroll
+          for (int k = 0; k < EB; ++k) {
+            unsigned tg = (k & 1) ? rv.z : rv.x, wb = (k & 1) ? rv.w : rv.y;
+            if constexpr (LP > 1) {
+              tg = __shfl_sync(0xffffffffu, tg, k >> 1, LP);
+              wb = __shfl_sync(0xffffffffu, wb, k >> 1, LP);
+            }
+            const int a = ab + k;
+            if (a >= A0 && a < A1) take(tg, wb);
+          }
+          rv = rn;
+        }
       }
       if (active) {
         const bool open_right = j1 < cnt && (int)(__ldg(&rec[j1].x) >> ebits) == cur;
