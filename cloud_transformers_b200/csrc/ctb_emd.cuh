@@ -212,7 +212,10 @@ emd_auction_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz
     const bool was_together = Kc > 1;
     if (was_together) cloud_sync();
     const int U = emd_xload<GLOBAL>((was_together ? m_cnts : cnts) + cur);
-    if (U == 0) break;
+    if (U == 0) {
+      if (!GLOBAL && was_together) cluster.sync();       // CTA 0 must not leave before everyone has read its count
+      break;
+    }
     // The number of unassigned sources never grows, so CTAs only ever leave.  A cluster stays whole until CTA 0 can
     // finish alone; the co-resident CTAs of the global variant thin out so that everyone left has > 4 sources.
     if (was_together) {
@@ -228,6 +231,7 @@ emd_auction_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz
         for (int i = threadIdx.x; i < nc; i += kEmdThreads) price[__ldcg(chg_t + i)] = __ldcg(chg_p + i);
         __syncthreads();
       }
+      if (!GLOBAL && want != Kc) cluster.sync();         // (everyone has read CTA 0's count before anyone moves on)
       Kc = want;
       if ((int)rank >= Kc) return;       // (nothing reads this CTA's shared memory)
     }
@@ -320,26 +324,25 @@ emd_auction_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz
         if (s < U) {
           const int j = (int)una[s];
           const int tg = emd_xload<GLOBAL>(bid + j);
-          if (last || (int)(0xffffffffu - (unsigned)(emd_xload<GLOBAL>(top + tg) & 0xffffffffull)) == j) {
+          if (last) {
+            asg[j] = (uint16_t)tg;                             // (:196-199: everybody left takes what it bid on)
+          } else if ((int)(0xffffffffu - (unsigned)(emd_xload<GLOBAL>(top + tg) & 0xffffffffull)) == j) {
             const unsigned prev = inv[tg];
-            if (!last && prev != 0xffffu) {
+            if (prev != 0xffffu) {
               asg[prev] = 0xffffu;
               push = (int)prev;
             }
             inv[tg] = (uint16_t)j;
             asg[j] = (uint16_t)tg;
-            if (!last) {
-              const float np_ = __fadd_rn(gprice[tg], emd_xload<GLOBAL>(binc + j));
-              gprice[tg] = np_;
-              if (GLOBAL) {
-                price[tg] = np_;
-                if (together) {
-                  const int ci = atomicAdd(cnts + 2, 1);
-                  chg_t[ci] = tg;
-                  chg_p[ci] = np_;
-                }
+            const float np_ = __fadd_rn(gprice[tg], emd_xload<GLOBAL>(binc + j));
+            gprice[tg] = np_;
+            if (GLOBAL) {
+              price[tg] = np_;
+              if (together) {
+                const int ci = atomicAdd(cnts + 2, 1);
+                chg_t[ci] = tg;
+                chg_p[ci] = np_;
               }
-              top[tg] = 0ull;
             }
           } else {
             push = j;
@@ -354,6 +357,15 @@ emd_auction_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz
         }
       }
       __syncthreads();
+      // the targets that were bid on are open for bids again (after every loser has read the winning bid)
+      if (!last) {
+        for (int s = threadIdx.x; s < U; s += kEmdThreads) {
+          const int j = (int)una[s];
+          const int tg = emd_xload<GLOBAL>(bid + j);
+          if (asg[j] == (uint16_t)tg && inv[tg] == (uint16_t)j) top[tg] = 0ull;
+        }
+        __syncthreads();
+      }
     }
   }
   if (rank != 0) return;
