@@ -333,6 +333,7 @@ def run_ours(args):
     del data, paths
     torch.cuda.empty_cache()
     others = run_other_configs(args, dev) if (rank == 0 and "others" not in skip) else None
+    losses = run_losses(dev) if (rank == 0 and "losses" not in skip) else None
     barrier()
     train = train_eager = train_fused = train_nccl = None
     if args.train_steps > 0 and "train" not in skip:
@@ -378,6 +379,7 @@ def run_ours(args):
             "bf16_grid_mode": bf16_mode,
             "deterministic_mode": det_mode,
             "other_configs": others,
+            "completion_losses": losses,
         }
         print(json.dumps(line))
     if world > 1:
@@ -525,6 +527,41 @@ def _barrier(world):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+
+
+def run_losses(dev):
+    """Row N3: the completion losses at the shapes of train_inpainter.py:187-192 / :267-269 (EMD eps 0.005 x 50 iterations
+    in training, 0.004 x 3000 in validation; clouds of 2048 and, from the inpainting decoder, 16384 points) and the
+    Chamfer distance, through the public modules, ms per call on this rank (the reference's own kernels on the same
+    GPU: profiles/r02_losses_vs_reference_kernels.txt)."""
+    import torch
+    from cloud_transformers_b200.chamfer import ChamferFunction
+    from cloud_transformers_b200.emd import emdModule
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(11)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return round(a.elapsed_time(b) / reps, 4)
+
+    try:
+        for B, n, eps, iters, reps in [(32, 2048, 0.005, 50, 5), (32, 2048, 0.004, 3000, 2), (2, 16384, 0.005, 50, 3)]:
+            x = torch.rand(B, n, 3, device=dev, generator=gen)
+            y = (x[:, torch.randperm(n, device=dev, generator=gen)] + 0.02 * torch.randn(B, n, 3, device=dev, generator=gen)).clamp(0, 1).contiguous()
+            out["emd_%dx%d_eps%g_%dit_ms" % (B, n, eps, iters)] = timed(lambda: emdModule()(x, y, eps, iters), reps)
+        for B, n, m in [(32, 2048, 2048), (8, 8192, 8192)]:
+            x, y = torch.rand(B, n, 3, device=dev, generator=gen), torch.rand(B, m, 3, device=dev, generator=gen)
+            out["chamfer_%dx%dx%d_ms" % (B, n, m)] = timed(lambda: ChamferFunction.apply(x, y), 5)
+    except Exception as exc:  # noqa: BLE001
+        out["unavailable"] = repr(exc)[:200]
+    return out
 
 
 def run_other_configs(args, dev):
@@ -841,7 +878,7 @@ def main():
                     help="bf16: grids (z, convolved, grad_grid, grad_z) stored as bf16, arithmetic stays fp32")
     ap.add_argument("--mode", default=os.environ.get("CTB_MODE", "auto"), choices=["auto", "atomic", "tile", "deterministic"])
     ap.add_argument("--skip", default="", help="developer switch: comma list of add-on sections to skip "
-                                               "(e2e, refgpu, det, others, train, eager, fusedbn, cpu, bf16)")
+                                               "(e2e, refgpu, det, others, losses, train, eager, fusedbn, cpu, bf16)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
