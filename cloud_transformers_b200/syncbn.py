@@ -83,7 +83,10 @@ class _SyncBNFn(torch.autograd.Function):
         ctx.save_for_backward(xc, weight, mean, invstd)
         ctx.ex_bwd = ex_bwd
         ctx.has_bias = bias is not None
-        return y                                   # (same shape as x; not a view: in-place ReLU may follow)
+        ctx.in_dtype = x.dtype
+        # same shape as x; not a view: in-place ReLU may follow.  Arithmetic is fp32; other input dtypes are converted
+        # on the way in and out, like nn.SyncBatchNorm returns its input's dtype.
+        return y if x.dtype == torch.float32 else y.to(x.dtype)
 
     @staticmethod
     @once_differentiable
@@ -98,6 +101,8 @@ class _SyncBNFn(torch.autograd.Function):
         with torch.cuda.device(xc.device):
             _call("ctb_syncbn_bwd", _ptr(xc), _ptr(gyc), _ptr(weight), _ptr(mean), _ptr(invstd), _ptr(gx), _ptr(gw), _ptr(gb),
                   ctypes.byref(ctx.ex_bwd), B, C, L, _stream(xc))
+        if ctx.in_dtype != torch.float32:
+            gx = gx.to(ctx.in_dtype)
         return gx, gw, gb, None, None, None, None, None, None
 
 

@@ -102,6 +102,15 @@ def main():
             res.append((yb.detach(), xi.grad, net[0].weight.grad, net[0].bias.grad, net[0].running_var.clone()))
         for a, b, what in zip(res[1], res[0], ("output", "input gradient", "grad weight", "grad bias", "running_var")):
             close(a, b, "%s of %s" % (what, shape), rel=2e-5)
+    # other input dtypes: converted on the way in and out (fp32 arithmetic), gradient in the input's dtype
+    hb = syncbn.convert_sync_batchnorm(nn.Sequential(nn.BatchNorm1d(12)).to(dev))
+    xh = (torch.randn(8, 12, 64, device=dev, generator=g) * (1 + rank)).half().requires_grad_(True)
+    yh = hb(xh)
+    assert yh.dtype == torch.float16
+    yh.float().square().sum().backward()
+    assert xh.grad.dtype == torch.float16 and torch.isfinite(xh.grad.float()).all()
+    with torch.no_grad():
+        close(yh.float(), hb(xh.detach().float()), "half input", rel=2e-3)
     # the layers replay inside a CUDA graph (device-side epochs, fixed pointers).  A fresh copy whose first backward
     # runs on the warm-up stream: gradient accumulators created on the legacy default stream cannot be captured
     ours = syncbn.convert_sync_batchnorm(copy.deepcopy(base))
