@@ -144,8 +144,14 @@ def test_dropin_resolves_inside_the_reference_tree():
         model = rt.load_model("model_zoo/scanobject/classifier.py")
         import layers.cloud_transform as ct
         import layers.multihead_ct as mh
+        import chamfer_extension.dist_chamfer as ch
+        import emd_linear.emd_module as em
         assert os.path.realpath(ct.__file__).startswith(os.path.realpath(RL.DROPIN_ROOT))
         assert os.path.realpath(mh.__file__).startswith(os.path.realpath(rt.root))
+        # the two loss modules of the completion scripts (train_inpainter.py:11-12) resolve to the drop-in as well
+        assert os.path.realpath(ch.__file__).startswith(os.path.realpath(RL.DROPIN_ROOT))
+        assert os.path.realpath(em.__file__).startswith(os.path.realpath(RL.DROPIN_ROOT))
+        assert hasattr(em, "emdModule") and hasattr(em, "emdFunction") and hasattr(ch, "ChamferDist")
         ours = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     assert ours == ref_keys
     assert sum(1 for k in ours if k.endswith("tensor_mod")) == 76
