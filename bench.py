@@ -334,6 +334,8 @@ def run_ours(args):
     torch.cuda.empty_cache()
     others = run_other_configs(args, dev) if (rank == 0 and "others" not in skip) else None
     losses = run_losses(dev) if (rank == 0 and "losses" not in skip) else None
+    completion = run_completion_train(dev) if (rank == 0 and "completion" not in skip and args.train_steps > 0) else None
+    torch.cuda.empty_cache()
     barrier()
     train = train_eager = train_fused = train_nccl = None
     if args.train_steps > 0 and "train" not in skip:
@@ -380,6 +382,7 @@ def run_ours(args):
             "deterministic_mode": det_mode,
             "other_configs": others,
             "completion_losses": losses,
+            "train_completion": completion,
         }
         print(json.dumps(line))
     if world > 1:
@@ -562,6 +565,64 @@ def run_losses(dev):
     except Exception as exc:  # noqa: BLE001
         out["unavailable"] = repr(exc)[:200]
     return out
+
+
+def run_completion_train(dev, steps=10):
+    """BASELINE config 4 (inpainting): the reference's own model_zoo/completion/inpainter.py (53.4 M parameters, AdaIN
+    blocks on 16384 decoder points) and the step of train_inpainter.py:176-196 -- partial_postproces on the host, EMD
+    (0.005, 50) + Chamfer, Adam 1e-4 -- through dropin/ (Splat / Slice, emd_linear.emd_module and
+    chamfer_extension.dist_chamfer are this library's), batch 2 as configs/inpainting.yaml, this rank only."""
+    import torch
+    try:
+        torch.manual_seed(42)
+        generator, root = load_reference_model_through_dropin("model_zoo/completion/inpainter.py")
+        import chamfer_extension.dist_chamfer as dist_chamfer
+        import emd_linear.emd_module as emd
+        from utils.pcd_utils import partial_postproces
+        n_params = sum(p.numel() for p in generator.parameters())
+        generator = generator.to(dev).train()
+        optimizer = torch.optim.Adam(generator.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.0)
+        EMD = emd.emdModule()
+        B, n_in, n_gt = 2, 2048, 16384
+        g = torch.Generator().manual_seed(3)
+        u = torch.randn(B, n_gt, 3, generator=g)
+        gt = (0.5 * u / u.norm(dim=-1, keepdim=True) * torch.tensor([1.0, 0.6, 0.4])).pin_memory()
+        partial = gt[:, :n_in].clone()
+        partial[:, 1500:] = 0.0
+        last = [None]
+
+        def step():
+            pcd_gt = 2 * gt.permute(0, 2, 1)[:, :, None].to(dev, non_blocking=True)
+            pcd_part_enc, pcd_part_noise = partial_postproces(2 * partial, pcd_gt.shape[-1])
+            pcd_part_enc = pcd_part_enc.permute(0, 2, 1)[:, :, None].to(dev)
+            pcd_part_noise = pcd_part_noise.permute(0, 2, 1).to(dev)
+            reconstruction, _ = generator(pcd_part_noise, pcd_part_enc)
+            dist, _ = EMD(reconstruction[:, :, 0].permute(0, 2, 1), pcd_gt[:, :, 0].permute(0, 2, 1), 0.005, 50)
+            loss_emd = torch.sqrt(dist).mean(1).mean()
+            loss_chamfer = dist_chamfer.loss_chamfer(reconstruction, pcd_gt)
+            loss = loss_emd + 0.0 * loss_chamfer                  # chamfer_weight 0.0, configs/inpainting.yaml:24
+            loss.backward()
+            optimizer.step()
+            optimizer.zero_grad()
+            last[0] = loss.item()                                 # the script logs it every step (:200-207)
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"samples_per_s": round(B / (ms * 1e-3), 2), "ms_per_step": round(ms, 2), "batch": B, "input_points": n_in,
+                "decoder_points": n_gt, "params_m": round(n_params / 1e6, 2), "steps": steps, "final_loss": round(last[0], 4),
+                "model": "model_zoo/completion/inpainter.py (reference file, unmodified) through dropin/",
+                "loop": "train_inpainter.py:176-196: host partial_postproces, EMD (0.005, 50 iterations) + Chamfer, Adam"}
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        return {"unavailable": repr(exc)[:300], "trace": traceback.format_exc()[-600:]}
 
 
 def run_other_configs(args, dev):
@@ -878,7 +939,7 @@ def main():
                     help="bf16: grids (z, convolved, grad_grid, grad_z) stored as bf16, arithmetic stays fp32")
     ap.add_argument("--mode", default=os.environ.get("CTB_MODE", "auto"), choices=["auto", "atomic", "tile", "deterministic"])
     ap.add_argument("--skip", default="", help="developer switch: comma list of add-on sections to skip "
-                                               "(e2e, refgpu, det, others, losses, train, eager, fusedbn, cpu, bf16)")
+                                               "(e2e, refgpu, det, others, losses, completion, train, eager, fusedbn, cpu, bf16)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

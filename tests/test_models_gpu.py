@@ -169,3 +169,51 @@ def test_reference_block_through_dropin_matches_fixture(prefix):
         sd = {k.split("/sd/", 1)[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix + "/sd/")}
         module.load_state_dict(sd, strict=True)
         _run_block(module, g, prefix)
+
+
+def test_reference_inpainting_train_step_through_dropin():
+    """BASELINE config 4: the reference's completion model (model_zoo/completion/inpainter.py, 53.4 M parameters, the
+    AdaIN blocks at 16384 decoder points) and the training computation of train_inpainter.py:176-196 -- the reference's
+    own partial_postproces, the EMD (0.005, 50) and the Chamfer loss -- with layers.cloud_transform,
+    emd_linear.emd_module and chamfer_extension.dist_chamfer resolving to dropin/, every other file the reference's."""
+    _need_tree()
+    with RL.reference_tree(dropin=True) as rt:
+        torch.manual_seed(0)
+        generator = rt.load_model("model_zoo/completion/inpainter.py")
+        import chamfer_extension.dist_chamfer as dist_chamfer
+        import emd_linear.emd_module as emd
+        from utils.pcd_utils import partial_postproces
+        assert os.path.realpath(emd.__file__).startswith(os.path.realpath(RL.DROPIN_ROOT))
+        assert os.path.realpath(dist_chamfer.__file__).startswith(os.path.realpath(RL.DROPIN_ROOT))
+        assert abs(sum(p.numel() for p in generator.parameters()) / 1e6 - 53.41) < 0.01
+        generator = generator.to(DEV).train()
+        optimizer = torch.optim.Adam(generator.parameters(), lr=1e-4)
+        EMD = emd.emdModule()
+        B, n_in, n_gt = 2, 2048, 16384                           # configs/inpainting.yaml
+        g = torch.Generator().manual_seed(3)
+        u = torch.randn(B, n_gt, 3, generator=g)
+        gt = 0.5 * u / u.norm(dim=-1, keepdim=True) * torch.tensor([1.0, 0.6, 0.4])      # points on an ellipsoid in [-0.5, 0.5]^3
+        partial = gt[:, :n_in].clone()
+        partial[:, 1500:] = 0.0                                  # zero rows = padding, dropped by partial_postproces
+        losses = []
+        for step in range(3):
+            pcd_gt = 2 * gt.permute(0, 2, 1)[:, :, None].to(DEV)
+            pcd_part_enc, pcd_part_noise = partial_postproces(2 * partial, pcd_gt.shape[-1])
+            pcd_part_enc = pcd_part_enc.permute(0, 2, 1)[:, :, None].to(DEV)
+            pcd_part_noise = pcd_part_noise.permute(0, 2, 1).to(DEV)
+            reconstruction, lattices_sizes = generator(pcd_part_noise, pcd_part_enc)
+            assert reconstruction.shape == (B, 3, 1, n_gt)
+            dist, assignment = EMD(reconstruction[:, :, 0].permute(0, 2, 1), pcd_gt[:, :, 0].permute(0, 2, 1), 0.005, 50)
+            loss_emd = torch.sqrt(dist).mean(1).mean()
+            loss_chamfer = dist_chamfer.loss_chamfer(reconstruction, pcd_gt)
+            loss = loss_emd + 0.1 * loss_chamfer
+            loss.backward()
+            grads = [p.grad for p in generator.parameters() if p.grad is not None]
+            assert len(grads) > 100 and all(torch.isfinite(gr).all() for gr in grads)
+            assert float(sum(gr.abs().sum() for gr in grads)) > 0.0
+            optimizer.step()
+            optimizer.zero_grad()
+            assert int(assignment.min()) >= 0 and int(assignment.max()) < n_gt
+            assert assignment.unique().numel() > n_gt // 2        # most of the targets are matched after 50 iterations
+            losses.append(float(loss.detach()))
+        assert all(np.isfinite(losses)), losses
