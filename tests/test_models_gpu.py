@@ -217,3 +217,82 @@ def test_reference_inpainting_train_step_through_dropin():
             assert assignment.unique().numel() > n_gt // 2        # most of the targets are matched after 50 iterations
             losses.append(float(loss.detach()))
         assert all(np.isfinite(losses)), losses
+
+
+def _load_pair(rel_path):
+    """The same reference model file twice, same seed: on the reference's own torch ops and through dropin/."""
+    with RL.reference_tree(dropin=False) as rt:
+        torch.manual_seed(0)
+        ref = rt.load_model(rel_path)
+    with RL.reference_tree(dropin=True) as rt:
+        torch.manual_seed(0)
+        ours = rt.load_model(rel_path)
+        import layers.cloud_transform as ct
+        assert os.path.realpath(ct.__file__).startswith(os.path.realpath(RL.DROPIN_ROOT))
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    return ref.to(DEV).train(), ours.to(DEV).train()
+
+
+def _compare_models(ref, ours, make_args, pick, what):
+    """Same input through both (train mode, dropout off, BatchNorm on batch statistics): outputs and gradients."""
+    dropout_off(ref), dropout_off(ours)
+    # (TF32 convolutions round their inputs to 10 bits: a 1e-7 difference between the two paths would come out as 1e-4)
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    outs = []
+    for model in (ref, ours):
+        args, leaf = make_args()
+        out = pick(model(*args))
+        w = torch.randn(out.shape, generator=torch.Generator().manual_seed(5)).to(DEV)
+        (out * w).sum().backward()
+        first = next(p for n, p in model.named_parameters() if n.startswith("first_process.0.weight"))
+        outs.append((out.detach().cpu().numpy(), leaf.grad.cpu().numpy(), first.grad.cpu().numpy()))
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    close(outs[1][0], outs[0][0], what + ": output")
+    close_l2(outs[1][1], outs[0][1], what + ": d loss / d input", rel=2e-2)
+    close_l2(outs[1][2], outs[0][2], what + ": grad first conv", rel=2e-2)
+
+
+def test_reference_s3dis_segmenter_through_dropin_matches_reference_ops_on_gpu():
+    """BASELINE config 3: model_zoo/s3dis/segmenter.py (9.22 M parameters; train_segmentation.py:180-186, N = 4096, xyz +
+    rgb) -- the reference's torch composition of Splat / Slice on the GPU against the B200 kernels, model level."""
+    _need_tree()
+    ref, ours = _load_pair("model_zoo/s3dis/segmenter.py")
+
+    def make_args():
+        g = torch.Generator().manual_seed(9)
+        pcd = torch.cat([torch.rand(2, 2, 4096, generator=g), 3 * torch.rand(2, 1, 4096, generator=g),
+                         torch.rand(2, 3, 4096, generator=g)], dim=1)[:, :, None].to(DEV).requires_grad_(True)
+        return (pcd,), pcd
+
+    _compare_models(ref, ours, make_args, lambda o: o[0], "s3dis segmenter")
+
+
+def test_reference_padded_segmenter_through_dropin_matches_reference_ops_on_gpu():
+    """model_zoo/s3dis/segmenter_pad.py: ragged clouds with a padding mask through every block (multihead_ct.py:84-107)."""
+    _need_tree()
+    ref, ours = _load_pair("model_zoo/s3dis/segmenter_pad.py")
+
+    def make_args():
+        g = torch.Generator().manual_seed(10)
+        pts = (torch.rand(2, 3000, 3, generator=g) * 2 - 1).to(DEV)
+        pad = torch.ones(2, 3000)
+        pad[0, 2500:] = 0.0
+        pad[1, 1777:] = 0.0
+        feats = torch.rand(2, 4, 3000, generator=g).to(DEV).requires_grad_(True)
+        return (pts, pad.to(DEV), feats), feats
+
+    _compare_models(ref, ours, make_args, lambda o: o, "padded segmenter")
+
+
+def test_reference_classifier_with_scales_through_dropin_matches_reference_ops_on_gpu():
+    """model_zoo/scanobject/classifier_scales.py: the learnable per-axis scales of the lattice transforms."""
+    _need_tree()
+    ref, ours = _load_pair("model_zoo/scanobject/classifier_scales.py")
+
+    def make_args():
+        g = torch.Generator().manual_seed(11)
+        pcd = (torch.rand(4, 3, 1, 2048, generator=g) * 2 - 1).to(DEV).requires_grad_(True)
+        return (pcd,), pcd
+
+    _compare_models(ref, ours, make_args, lambda o: o[0], "classifier with scales")
