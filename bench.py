@@ -336,6 +336,8 @@ def run_ours(args):
     losses = run_losses(dev) if (rank == 0 and "losses" not in skip) else None
     completion = run_completion_train(dev) if (rank == 0 and "completion" not in skip and args.train_steps > 0) else None
     torch.cuda.empty_cache()
+    s3dis = run_s3dis_train(dev) if (rank == 0 and "s3dis" not in skip and args.train_steps > 0) else None
+    torch.cuda.empty_cache()
     barrier()
     train = train_eager = train_fused = train_nccl = None
     if args.train_steps > 0 and "train" not in skip:
@@ -383,6 +385,7 @@ def run_ours(args):
             "other_configs": others,
             "completion_losses": losses,
             "train_completion": completion,
+            "train_s3dis": s3dis,
         }
         print(json.dumps(line))
     if world > 1:
@@ -620,6 +623,56 @@ def run_completion_train(dev, steps=10):
                 "decoder_points": n_gt, "params_m": round(n_params / 1e6, 2), "steps": steps, "final_loss": round(last[0], 4),
                 "model": "model_zoo/completion/inpainter.py (reference file, unmodified) through dropin/",
                 "loop": "train_inpainter.py:176-196: host partial_postproces, EMD (0.005, 50 iterations) + Chamfer, Adam"}
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        return {"unavailable": repr(exc)[:300], "trace": traceback.format_exc()[-600:]}
+
+
+def run_s3dis_train(dev, steps=20):
+    """BASELINE config 3 (S3DIS 1x1): the reference's own model_zoo/s3dis/segmenter.py (9.22 M parameters) and the step
+    of train_segmentation.py:177-200 -- clouds of 4096 points with xyz + rgb from pinned host memory, per-point cross
+    entropy over 13 classes, Adam 1e-3, the loss and the arg-max predictions read back every step -- through dropin/,
+    batch 8 as configs/s3dis.yaml, this rank only."""
+    import torch
+    try:
+        torch.manual_seed(42)
+        generator, root = load_reference_model_through_dropin("model_zoo/s3dis/segmenter.py")
+        n_params = sum(p.numel() for p in generator.parameters())
+        generator = generator.to(dev).train()
+        optimizer = torch.optim.Adam(generator.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.0)
+        ce = torch.nn.CrossEntropyLoss()
+        B, N = 8, 4096
+        g = torch.Generator().manual_seed(4)
+        clouds = [torch.cat([torch.rand(B, N, 2, generator=g), 3 * torch.rand(B, N, 1, generator=g),
+                             torch.rand(B, N, 3, generator=g)], dim=2).pin_memory() for _ in range(4)]
+        labels = [torch.randint(0, 13, (B, N), generator=g).pin_memory() for _ in range(4)]
+        last = [None]
+
+        def step(i):
+            pcd = clouds[i % 4].to(dev, non_blocking=True).permute(0, 2, 1)[:, :, None]
+            lab = labels[i % 4].to(dev, non_blocking=True)
+            pred, _ = generator(pcd)
+            loss = ce(pred[:, :, 0], lab)
+            loss.backward()
+            optimizer.step()
+            optimizer.zero_grad()
+            last[0] = loss.item()
+            pred[:, :, 0].detach().cpu().numpy().argmax(1)          # confusion-matrix update of the script (:198-200)
+
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"samples_per_s": round(B / (ms * 1e-3), 2), "ms_per_step": round(ms, 2), "batch": B, "points": N,
+                "params_m": round(n_params / 1e6, 2), "steps": steps, "final_loss": round(last[0], 4),
+                "model": "model_zoo/s3dis/segmenter.py (reference file, unmodified) through dropin/",
+                "loop": "train_segmentation.py:177-200: per-point cross entropy, Adam, loss and predictions read back every step"}
     except Exception as exc:  # noqa: BLE001
         import traceback
         return {"unavailable": repr(exc)[:300], "trace": traceback.format_exc()[-600:]}
@@ -939,7 +992,7 @@ def main():
                     help="bf16: grids (z, convolved, grad_grid, grad_z) stored as bf16, arithmetic stays fp32")
     ap.add_argument("--mode", default=os.environ.get("CTB_MODE", "auto"), choices=["auto", "atomic", "tile", "deterministic"])
     ap.add_argument("--skip", default="", help="developer switch: comma list of add-on sections to skip "
-                                               "(e2e, refgpu, det, others, losses, completion, train, eager, fusedbn, cpu, bf16)")
+                                               "(e2e, refgpu, det, others, losses, completion, s3dis, train, eager, fusedbn, cpu, bf16)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
