@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CTB_VERSION 100 /* major*100 + minor */
+#define CTB_VERSION 200 /* major*100 + minor; 2.0: plan argument of ctb_slice_fwd_keys, EMD, SyncBN, Chamfer entries */
 
 typedef enum ctb_status {
   CTB_OK = 0,
