@@ -24,7 +24,8 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libctb200.so does not export %s" % name
     assert sorted(_lib.SIGNATURES) == declared, "ctypes signatures out of sync with the header"
-    assert lib.ctb_version() == 100
+    header = open(os.path.join(ROOT, "include", "ctb200.h")).read()
+    assert lib.ctb_version() == int(re.search(r"#define CTB_VERSION (\d+)", header).group(1)) == 200
     assert lib.ctb_strerror(-2) == b"unsupported shape"
 
 
